@@ -1,0 +1,128 @@
+"""Build + ctypes loader for libcdseg_b200.so (the C-ABI CUDA library, include/cdseg_b200.h).
+
+The library is built IN-TREE (cdsegnet_b200/libcdseg_b200.so) with nvcc for sm_100a only.
+There is deliberately no CPU fallback: if the library is missing or a call fails the
+product path raises.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-cudart", "shared"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ for sm_100a into one shared library."""
+    if not force and not needs_build():
+        return LIB_PATH
+    objs = []
+    bdir = os.path.join(_HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(bdir, s.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
+        if verbose and out.strip():
+            print(out)
+    cmd = [_nvcc(), "-shared", "-cudart", "shared", "-o", LIB_PATH] + objs
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return LIB_PATH
+
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_int64
+_F = ctypes.c_float
+_Z = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol declared in include/cdseg_b200.h
+SIGNATURES = {
+    "cdseg_abi_version": (_I, []),
+    "cdseg_launch_count": (ctypes.c_ulonglong, []),
+    "cdseg_launch_count_reset": (None, []),
+    "cdseg_grid_max": (_I, [_P, _L, _P, _P]),
+    "cdseg_offset2batch": (_I, [_P, _I, _L, _P, _P]),
+    "cdseg_encode_codes": (_I, [_P, _P, _L, _I, ctypes.POINTER(_I), _I, _P, _P]),
+    "cdseg_debug_encode_host": (_I, [_P, _P, _L, _I, _I, _P]),
+    "cdseg_argsort_workspace_bytes": (_Z, [_I, _L]),
+    "cdseg_argsort_rows": (_I, [_P, _I, _L, _I, _P, _P, _P, _Z, _P]),
+    "cdseg_patch_count": (_I, [ctypes.POINTER(_L), _I, _I, ctypes.POINTER(_I)]),
+    "cdseg_patch_maps": (_I, [_P, ctypes.POINTER(_L), _I, _I, _I, _P, _P, _P, _P, _P]),
+    "cdseg_pool_plan_workspace_bytes": (_Z, [_I, _L]),
+    "cdseg_pool_plan": (_I, [_P, _P, _I, _L, _P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _Z, _P]),
+    "cdseg_pool_reduce": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _I, _P, _P, _P]),
+    "cdseg_unpool_add": (_I, [_P, _P, _P, _L, _I, _F, _P, _P]),
+    "cdseg_nbr_workspace_bytes": (_Z, [_L]),
+    "cdseg_hash_capacity": (_L, [_L]),
+    "cdseg_nbr_build": (_I, [_P, _P, _L, _I, _P, _P, _Z, _P]),
+    "cdseg_subm_conv": (_I, [_P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _P, _P]),
+    "cdseg_attn_pack_f16": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "cdseg_attn_pack_f32": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "cdseg_attn_tc_smem_bytes": (_Z, [_I]),
+    "cdseg_attn_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
+    "cdseg_attn_exact": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
+    "cdseg_add_layernorm": (_I, [_P, _P, _P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),
+    "cdseg_scale_shift_act": (_I, [_P, _P, _P, _I, _L, _I, _P, _P]),
+    "cdseg_small_linear": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "cdseg_rows_uniform": (_I, [_P, _P, _P, _L, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and bind every entry point.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the cdsegnet_b200 hot path)")
+    import torch  # noqa: F401  (loads libcudart.so.12 first so both sides share one CUDA runtime)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class CdsegError(RuntimeError):
+    pass
+
+
+def check(status, what):
+    if status != 0:
+        kind = {-1: "invalid argument", -2: "workspace too small"}.get(status, f"CUDA error {status}")
+        raise CdsegError(f"{what}: {kind}")

@@ -1,0 +1,164 @@
+// Patch gather ("qkv[order]") for serialized attention, plus the exact fp32 SIMT
+// attention used as the high-precision mode.
+//
+// Reference: pointcept/models/point_transformer_v3/point_transformer_v3m1_base.py
+//   :258-262  order = serialized_order[k][pad]; qkv = self.qkv(feat)[order]
+//   :264-280  dense branch: softmax((q*scale) @ k^T) @ v per (patch, head)     <- fp32 semantics
+//   :282-289  flash branch: qkv.half(), varlen over cu_seqlens                 <- fp16 semantics (attn_tc.cu)
+//   :290      feat = feat[inverse]
+//   :1003-1047 cross attention: q rows by q_order, kv rows by kv_order[q_pad]
+//
+// Packed layout (per tensor Q, K, V): [H][T][Kp][16] where the innermost [Kp][16] block of
+// one (head, patch) is stored as 8x8 "core matrices": element (r, d) lives at
+//   (r/8)*128 + (d/8)*64 + (r%8)*8 + (d%8)          (in elements)
+// i.e. exactly the shared-memory image tcgen05.mma's no-swizzle descriptors want
+// (K-major for Q and K, MN-major for V), so the attention kernel stages whole tiles
+// with plain 1-D bulk copies.  Slots with slot_src < 0 are zero rows.
+#include "common.cuh"
+
+// src: fp32 rows [n, ld] ; column block for (which, h) starts at col0 + which*C + h*16
+template <typename OutT>
+__global__ void pack_heads_kernel(const float* __restrict__ src, int64_t ld, int col0, int C, int nwhich,
+                                  const int32_t* __restrict__ slot_src, int H, int T, int Kp,
+                                  OutT* __restrict__ dst0, OutT* __restrict__ dst1, OutT* __restrict__ dst2) {
+  // consecutive threads -> consecutive slots (16-byte stores of 8 consecutive rows coalesce)
+  const int64_t slots = (int64_t)T * Kp;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (tid >= slots * H * nwhich) return;
+  const int64_t p = tid % slots;
+  const int h = (int)((tid / slots) % H);
+  const int which = (int)(tid / (slots * H));
+  const int t = (int)(p / Kp), r = (int)(p % Kp);
+  const int32_t s = slot_src[p];
+  float v[16];
+  if (s >= 0) {
+    const float4* row = reinterpret_cast<const float4*>(src + (int64_t)s * ld + col0 + which * C + h * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float4 q = row[j]; v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  }
+  OutT* dst = which == 0 ? dst0 : (which == 1 ? dst1 : dst2);
+  OutT* blk = dst + ((int64_t)h * T + t) * Kp * 16;
+  if constexpr (sizeof(OutT) == 2) {
+    __half2 hh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    uint4* o = reinterpret_cast<uint4*>(blk + (r / 8) * 128 + (r % 8) * 8);
+    o[0] = *reinterpret_cast<uint4*>(&hh[0]);       // d 0..7
+    o[8] = *reinterpret_cast<uint4*>(&hh[4]);       // d 8..15  (+64 elements = +8 uint4)
+  } else {
+    float4* o = reinterpret_cast<float4*>(blk + (int64_t)r * 16);   // exact mode: plain [Kp][16] fp32 rows
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+}
+
+// fp16 core-matrix packing.  src rows are fp32 [n, ld]; nwhich tensors (1..3) are taken from
+// column blocks col0 + w*C.  dst pointers beyond nwhich are ignored.
+CDSEG_API int cdseg_attn_pack_f16(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src,
+                                  int H, int T, int Kp, void* dst0, void* dst1, void* dst2, void* stream) {
+  if (H <= 0 || C != H * 16 || nwhich < 1 || nwhich > 3 || (Kp % 128) || (ld & 3) || (col0 & 3)) return CDSEG_EINVAL;
+  const int64_t total = (int64_t)T * Kp * H * nwhich;
+  if (total == 0) return CDSEG_OK;
+  pack_heads_kernel<__half><<<cdseg_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, ld, col0, C, nwhich, slot_src, H, T, Kp, (__half*)dst0, (__half*)dst1, (__half*)dst2);
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
+
+CDSEG_API int cdseg_attn_pack_f32(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src,
+                                  int H, int T, int Kp, float* dst0, float* dst1, float* dst2, void* stream) {
+  if (H <= 0 || C != H * 16 || nwhich < 1 || nwhich > 3 || (Kp % 128) || (ld & 3) || (col0 & 3)) return CDSEG_EINVAL;
+  const int64_t total = (int64_t)T * Kp * H * nwhich;
+  if (total == 0) return CDSEG_OK;
+  pack_heads_kernel<float><<<cdseg_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, col0, C, nwhich, slot_src, H,
+                                                                                      T, Kp, dst0, dst1, dst2);
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// exact fp32 attention (SIMT): one thread per query row, keys streamed through shared memory
+// in tiles of 32 with one online-softmax rescale per tile.  Output rows are scattered straight
+// to the original point order (fuses "feat[inverse]").
+// ---------------------------------------------------------------------------------
+constexpr int AX_KT = 32;
+
+__global__ void __launch_bounds__(128) attn_exact_kernel(const float* __restrict__ Q, const float* __restrict__ K,
+                                                         const float* __restrict__ V,
+                                                         const int32_t* __restrict__ patch_len,
+                                                         const int32_t* __restrict__ slot_dst, int H, int T, int Kp,
+                                                         float scale, float* __restrict__ out, int64_t out_ld) {
+  __shared__ float sK[AX_KT][16];
+  __shared__ float sV[AX_KT][16];
+  const int qt = blockIdx.x, t = blockIdx.y, h = blockIdx.z;
+  const int len = patch_len[t];
+  if (qt * 128 >= len) return;
+  const int64_t blk = ((int64_t)h * T + t) * Kp * 16;
+  const int r = qt * 128 + threadIdx.x;
+  float q[16], acc[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 x = reinterpret_cast<const float4*>(Q + blk + (int64_t)r * 16)[j];
+    q[4 * j] = x.x * scale; q[4 * j + 1] = x.y * scale; q[4 * j + 2] = x.z * scale; q[4 * j + 3] = x.w * scale;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < len; k0 += AX_KT) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < AX_KT * 4; j += 128) {
+      const int kr = j / 4, kc = j % 4;
+      reinterpret_cast<float4*>(&sK[kr][0])[kc] = reinterpret_cast<const float4*>(K + blk + (int64_t)(k0 + kr) * 16)[kc];
+      reinterpret_cast<float4*>(&sV[kr][0])[kc] = reinterpret_cast<const float4*>(V + blk + (int64_t)(k0 + kr) * 16)[kc];
+    }
+    __syncthreads();
+    float s[AX_KT];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < AX_KT; ++j) {
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) d = fmaf(q[c], sK[j][c], d);
+      s[j] = (k0 + j < len) ? d : -INFINITY;
+      tmax = fmaxf(tmax, s[j]);
+    }
+    const float mn = fmaxf(m, tmax);
+    const float corr = __expf(m - mn);      // m = -inf on the first tile -> 0
+    l *= corr;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] *= corr;
+#pragma unroll
+    for (int j = 0; j < AX_KT; ++j) {
+      const float p = expf(s[j] - mn);
+      l += p;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = fmaf(p, sV[j][c], acc[c]);
+    }
+    m = mn;
+  }
+  const int32_t dst = slot_dst[(int64_t)t * Kp + r];
+  if (dst >= 0) {
+    const float inv = 1.f / l;
+    float4* o = reinterpret_cast<float4*>(out + (int64_t)dst * out_ld + h * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
+  }
+}
+
+// Q,K,V: fp32 [H][T][Kp][16] (cdseg_attn_pack_f32).  out: fp32 [n, out_ld], head h -> columns h*16..
+CDSEG_API int cdseg_attn_exact(const float* Q, const float* K, const float* V, const int32_t* patch_len,
+                               const int32_t* slot_dst, int H, int T, int Kp, float scale, float* out, int64_t out_ld,
+                               void* stream) {
+  if (H <= 0 || T < 0 || (Kp % 128) || (out_ld & 3)) return CDSEG_EINVAL;
+  if (T == 0) return CDSEG_OK;
+  dim3 g(Kp / 128, T, H);
+  attn_exact_kernel<<<g, 128, 0, (cudaStream_t)stream>>>(Q, K, V, patch_len, slot_dst, H, T, Kp, scale, out, out_ld);
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}

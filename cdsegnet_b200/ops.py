@@ -1,0 +1,225 @@
+"""torch-tensor wrappers over the C-ABI kernels (include/cdseg_b200.h).
+
+torch is used here for device memory and streams only: every wrapper allocates the
+outputs (caller-allocates convention of the C ABI), passes raw device pointers and
+the current CUDA stream, and raises on a non-zero status.  No wrapper synchronises.
+"""
+import ctypes
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+ORDER_IDS = {"z": 0, "z-trans": 1, "hilbert": 2, "hilbert-trans": 3}
+
+
+def _p(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.CdsegError("cdsegnet_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise _lib.CdsegError("tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.CdsegError(f"expected {dtype}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------- serialization
+def grid_max(grid):
+    out = torch.empty(1, dtype=torch.int32, device=grid.device)
+    check(_lib.load().cdseg_grid_max(_p(grid, torch.int32), grid.numel(), _p(out), _stream()), "grid_max")
+    return out
+
+
+def offset2batch(offset, n):
+    batch = torch.empty(n, dtype=torch.int32, device=offset.device)
+    check(_lib.load().cdseg_offset2batch(_p(offset, torch.int64), offset.numel(), n, _p(batch), _stream()), "offset2batch")
+    return batch
+
+
+def encode_codes(grid, batch, depth, orders):
+    n = grid.shape[0]
+    k = len(orders)
+    ids = (ctypes.c_int * k)(*[ORDER_IDS[o] for o in orders])
+    codes = torch.empty((k, n), dtype=torch.int64, device=grid.device)
+    check(_lib.load().cdseg_encode_codes(_p(grid, torch.int32), _p(batch, torch.int32), n, depth, ids, k, _p(codes), _stream()),
+          "encode_codes")
+    return codes
+
+
+def argsort_rows(codes, nbits):
+    k, n = codes.shape
+    lib = _lib.load()
+    order = torch.empty((k, n), dtype=torch.int32, device=codes.device)
+    inverse = torch.empty((k, n), dtype=torch.int32, device=codes.device)
+    nb = lib.cdseg_argsort_workspace_bytes(k, n)
+    ws = _ws(nb, codes.device)
+    check(lib.cdseg_argsort_rows(_p(codes, torch.int64), k, n, nbits, _p(order), _p(inverse), _p(ws), nb, _stream()),
+          "argsort_rows")
+    return order, inverse
+
+
+def patch_maps(order_row, scene_count, K):
+    """order_row int32 [n] (one curve).  Returns dict(slot_src, slot_dst, point_slot, patch_len, T, Kp)."""
+    lib = _lib.load()
+    B = len(scene_count)
+    cnt = (ctypes.c_int64 * B)(*[int(c) for c in scene_count])
+    T = ctypes.c_int(0)
+    check(lib.cdseg_patch_count(cnt, B, K, ctypes.byref(T)), "patch_count")
+    T = T.value
+    Kp = (K + 127) // 128 * 128
+    dev = order_row.device
+    n = int(sum(int(c) for c in scene_count))
+    slot_src = torch.empty(T * Kp, dtype=torch.int32, device=dev)
+    slot_dst = torch.empty(T * Kp, dtype=torch.int32, device=dev)
+    point_slot = torch.empty(n, dtype=torch.int32, device=dev)
+    patch_len = torch.empty(T, dtype=torch.int32, device=dev)
+    check(lib.cdseg_patch_maps(_p(order_row, torch.int32), cnt, B, K, Kp, _p(slot_src), _p(slot_dst), _p(point_slot),
+                               _p(patch_len), _stream()), "patch_maps")
+    return dict(slot_src=slot_src, slot_dst=slot_dst, point_slot=point_slot, patch_len=patch_len, T=T, Kp=Kp, K=K)
+
+
+# ---------------------------------------------------------------- pooling
+def pool_plan(code, order, n_dev, n_host, c0, pooling_depth, grid, batch, B, cap_child):
+    """One sync-free pooling level.  code/order: [k, ld].  Returns the child arrays (capacity cap_child)."""
+    lib = _lib.load()
+    k, ld = code.shape
+    dev = code.device
+    cap_parent = ld
+    out = dict(
+        cluster=torch.empty(cap_parent, dtype=torch.int32, device=dev),
+        idx_ptr=torch.empty(cap_child + 1, dtype=torch.int32, device=dev),
+        head=torch.empty(cap_child, dtype=torch.int32, device=dev),
+        code=torch.empty((k, cap_child), dtype=torch.int64, device=dev),
+        order=torch.empty((k, cap_child), dtype=torch.int32, device=dev),
+        inverse=torch.empty((k, cap_child), dtype=torch.int32, device=dev),
+        grid=torch.empty((cap_child, 3), dtype=torch.int32, device=dev),
+        batch=torch.empty(cap_child, dtype=torch.int32, device=dev),
+        m_dev=torch.zeros(1, dtype=torch.int32, device=dev),
+        offset=torch.zeros(B, dtype=torch.int64, device=dev),
+    )
+    nb = lib.cdseg_pool_plan_workspace_bytes(k, ld)
+    ws = _ws(nb, dev)
+    check(lib.cdseg_pool_plan(_p(code, torch.int64), _p(order, torch.int32), k, ld, _p(n_dev), int(n_host), c0,
+                              pooling_depth, _p(grid, torch.int32), _p(batch, torch.int32), _p(out["cluster"]),
+                              _p(out["idx_ptr"]), _p(out["head"]), _p(out["code"]), _p(out["order"]),
+                              _p(out["inverse"]), cap_child, _p(out["grid"]), _p(out["batch"]), _p(out["m_dev"]),
+                              _p(out["offset"]), _p(ws), nb, _stream()), "pool_plan")
+    return out
+
+
+def pool_reduce(x, coord, members, idx_ptr, m, bn_scale=None, bn_shift=None, gelu=False):
+    C = x.shape[1]
+    out = torch.empty((m, C), dtype=torch.float32, device=x.device)
+    out_coord = torch.empty((m, 3), dtype=torch.float32, device=x.device) if coord is not None else None
+    check(_lib.load().cdseg_pool_reduce(_p(x, torch.float32), _p(coord), _p(members, torch.int32), _p(idx_ptr, torch.int32),
+                                        m, C, _p(bn_scale), _p(bn_shift), int(gelu), _p(out), _p(out_coord), _stream()),
+          "pool_reduce")
+    return out, out_coord
+
+
+def unpool_add(a, b, cluster, alpha=1.0):
+    n, C = a.shape
+    out = torch.empty_like(a)
+    check(_lib.load().cdseg_unpool_add(_p(a, torch.float32), _p(b, torch.float32), _p(cluster, torch.int32), n, C,
+                                       float(alpha), _p(out), _stream()), "unpool_add")
+    return out
+
+
+# ---------------------------------------------------------------- submanifold conv
+def nbr_build(grid, batch, ksize):
+    lib = _lib.load()
+    n = grid.shape[0]
+    nbr = torch.empty((n, ksize ** 3), dtype=torch.int32, device=grid.device)
+    nb = lib.cdseg_nbr_workspace_bytes(n)
+    ws = _ws(nb, grid.device)
+    check(lib.cdseg_nbr_build(_p(grid, torch.int32), _p(batch, torch.int32), n, ksize, _p(nbr), _p(ws), nb, _stream()),
+          "nbr_build")
+    return nbr
+
+
+def subm_conv(x, nbr, wt, bias, ksize, ep_scale=None, ep_shift=None, ep_gelu=False):
+    """wt: fp32 [k^3, Ci, Co] (tap-major transposed weight)."""
+    n, Ci = x.shape
+    Co = wt.shape[2]
+    out = torch.empty((n, Co), dtype=torch.float32, device=x.device)
+    check(_lib.load().cdseg_subm_conv(_p(x, torch.float32), _p(nbr, torch.int32), _p(wt, torch.float32), _p(bias),
+                                      _p(ep_scale), _p(ep_shift), int(ep_gelu), n, Ci, Co, ksize, _p(out), _stream()),
+          "subm_conv")
+    return out
+
+
+# ---------------------------------------------------------------- attention
+def attn_pack(src, col0, C, nwhich, pm, H, exact=False):
+    """Gather rows of src (fp32 [n, ld]) by pm['slot_src'] into per-(head, patch) tiles."""
+    lib = _lib.load()
+    T, Kp = pm["T"], pm["Kp"]
+    dt = torch.float32 if exact else torch.float16
+    bufs = [torch.empty((H, T, Kp, 16), dtype=dt, device=src.device) for _ in range(nwhich)]
+    ptrs = [_p(b) for b in bufs] + [None] * (3 - nwhich)
+    fn = lib.cdseg_attn_pack_f32 if exact else lib.cdseg_attn_pack_f16
+    check(fn(_p(src, torch.float32), src.shape[1], col0, C, nwhich, _p(pm["slot_src"]), H, T, Kp, *ptrs, _stream()),
+          "attn_pack")
+    return bufs
+
+
+def attn(q, k, v, pm, H, scale, n_out, exact=False):
+    """softmax(q k^T * scale) v per (patch, head); rows scattered to original point order."""
+    lib = _lib.load()
+    C = H * 16
+    out = torch.empty((n_out, C), dtype=torch.float32, device=q.device)
+    fn = lib.cdseg_attn_exact if exact else lib.cdseg_attn_tc
+    check(fn(_p(q), _p(k), _p(v), _p(pm["patch_len"]), _p(pm["slot_dst"]), H, pm["T"], pm["Kp"], float(scale), _p(out),
+             C, _stream()), "attn")
+    return out
+
+
+# ---------------------------------------------------------------- row-wise
+def add_layernorm(a, b=None, t=None, batch=None, gamma=None, beta=None, eps=1e-5, want_sum=True, want_ln=True):
+    n, C = a.shape
+    y = torch.empty_like(a) if want_sum else None
+    ln = torch.empty_like(a) if want_ln else None
+    check(_lib.load().cdseg_add_layernorm(_p(a, torch.float32), _p(b), _p(t), _p(batch), _p(gamma), _p(beta), float(eps),
+                                          n, C, _p(y), _p(ln), _stream()), "add_layernorm")
+    return y, ln
+
+
+def scale_shift_act(x, scale=None, shift=None, act=0):
+    n, C = x.shape
+    out = torch.empty_like(x)
+    check(_lib.load().cdseg_scale_shift_act(_p(x, torch.float32), _p(scale), _p(shift), act, n, C, _p(out), _stream()),
+          "scale_shift_act")
+    return out
+
+
+def small_linear(x, W, bias, act=0):
+    R, K = x.shape
+    O = W.shape[0]
+    out = torch.empty((R, O), dtype=torch.float32, device=x.device)
+    check(_lib.load().cdseg_small_linear(_p(x, torch.float32), _p(W, torch.float32), _p(bias), act, R, K, O, _p(out),
+                                         _stream()), "small_linear")
+    return out
+
+
+def rows_uniform_flag(x, batch, offset, flag):
+    n, C = x.shape
+    check(_lib.load().cdseg_rows_uniform(_p(x, torch.float32), _p(batch, torch.int32), _p(offset, torch.int64), n, C,
+                                         _p(flag), _stream()), "rows_uniform")
+
+
+def launch_count():
+    return int(_lib.load().cdseg_launch_count())
+
+
+def launch_count_reset():
+    _lib.load().cdseg_launch_count_reset()

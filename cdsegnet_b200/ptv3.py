@@ -1,0 +1,511 @@
+"""B200-native ``PT-v3m1`` backbone: the CDSegNet dual PTv3 network (Conditional Network =
+code prefix ``_n_*``, Noise Network = code prefix ``_c_*``, TransferModule ``_tm_dec0``)
+behind the reference's constructor signature, ``forward(c_point, n_point)`` contract and
+state_dict names (pointcept/models/point_transformer_v3/point_transformer_v3m1_base.py:1340-1846,
+abbreviated ptv3.py below), so released checkpoints load with ``strict=True``.
+
+Host code is plain PyTorch plumbing (module tree = parameter names; cuBLAS ``F.linear`` for
+the dense layers, as SURVEY.md §7.2 item 9 allows); the hot ops run in the in-tree C-ABI
+CUDA library (serialization, radix argsort, pooling plan/reduce, submanifold conv,
+tcgen05 patch attention, fused residual/LayerNorm/timestep kernels).  There is no CPU
+path: tensors must live on a CUDA device.
+
+Inference-only in this round (SSI forward, default.py:371-422); autograd through the
+custom kernels is the next §8(f) row.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .structure import Plan
+
+BN_EPS, BN_MOM = 1e-3, 0.01          # ptv3.py:1435
+
+
+class Point(dict):
+    """dict with attribute access standing in for pointcept's addict-based Point
+    (pointcept/models/utils/structure.py:14).  ``_level`` links to the GPU-side structure."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+class Seq(nn.Module):
+    """named container (parameter naming mirrors PointSequential, pointcept/models/modules.py:17-56)."""
+
+    def __init__(self, *mods, **named):
+        super().__init__()
+        for i, m in enumerate(mods):
+            self.add_module(str(i), m)
+        for k, m in named.items():
+            self.add_module(k, m)
+
+    def add(self, module, name=None):
+        self.add_module(name if name is not None else str(len(self._modules)), module)
+
+    def __getitem__(self, i):
+        return list(self._modules.values())[i]
+
+    def __len__(self):
+        return len(self._modules)
+
+
+class SubMConv3d(nn.Module):
+    """parameter holder with spconv's layout: weight [C_out, k, k, k, C_in], optional bias
+    (spconv.SubMConv3d at ptv3.py:356-362, 647-654).  Compute = cdseg_subm_conv."""
+
+    def __init__(self, cin, cout, kernel_size, bias=True):
+        super().__init__()
+        self.k, self.cin, self.cout = kernel_size, cin, cout
+        self.weight = nn.Parameter(torch.empty(cout, kernel_size, kernel_size, kernel_size, cin))
+        self.bias = nn.Parameter(torch.empty(cout)) if bias else None
+        fan_in = cin * kernel_size ** 3
+        nn.init.kaiming_uniform_(self.weight.view(cout, -1), a=math.sqrt(5))
+        if bias:
+            bound = 1 / math.sqrt(fan_in)
+            nn.init.uniform_(self.bias, -bound, bound)
+        self._wt = None
+
+    def wt(self):
+        """tap-major transposed copy [k^3, C_in, C_out] (rebuilt when the parameter changes)."""
+        key = (self.weight._version, self.weight.data_ptr(), self.weight.device)
+        if self._wt is None or self._wt[0] != key:
+            w = self.weight.detach().reshape(self.cout, self.k ** 3, self.cin).permute(1, 2, 0).contiguous().float()
+            self._wt = (key, w)
+        return self._wt[1]
+
+    def forward(self, x, level, ep_scale=None, ep_shift=None, ep_gelu=False):
+        b = self.bias.detach() if self.bias is not None else None
+        return ops.subm_conv(x, level.nbr(self.k), self.wt(), b, self.k, ep_scale, ep_shift, ep_gelu)
+
+
+def bn_fold(bn):
+    """eval-mode BatchNorm1d as per-channel scale/shift."""
+    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
+    shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
+    return scale, shift
+
+
+def _bn(c):
+    return nn.BatchNorm1d(c, eps=BN_EPS, momentum=BN_MOM)
+
+
+class MLP(nn.Module):
+    def __init__(self, c, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(c, hidden)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden, c)
+
+    def forward(self, x):
+        return self.fc2(F.gelu(self.fc1(x)))
+
+
+class SerializedAttention(nn.Module):
+    """ptv3.py:125-296 (flash-branch semantics; ``exact`` selects fp32 dense-branch numerics)."""
+
+    def __init__(self, channels, num_heads, patch_size, qkv_bias=True, qk_scale=None, order_index=0):
+        super().__init__()
+        assert channels % num_heads == 0
+        if channels // num_heads != 16:
+            raise NotImplementedError("cdsegnet_b200 attention kernels are specialised for head_dim 16 "
+                                      "(every shipped CDSegNet config, configs/scannet/CDSegNet.py:66-82)")
+        self.channels, self.num_heads, self.patch_size = channels, num_heads, patch_size
+        self.scale = qk_scale or (channels // num_heads) ** -0.5
+        self.order_index = order_index
+        self.qkv = nn.Linear(channels, channels * 3, bias=qkv_bias)
+        self.proj = nn.Linear(channels, channels)
+
+    def forward(self, x, level, exact):
+        pm = level.patch_maps(self.order_index, self.patch_size)
+        qkv = self.qkv(x)
+        q, k, v = ops.attn_pack(qkv, 0, self.channels, 3, pm, self.num_heads, exact)
+        o = ops.attn(q, k, v, pm, self.num_heads, self.scale, x.shape[0], exact)
+        return self.proj(o)
+
+
+class Block(nn.Module):
+    """ptv3.py:325-428 (pre_norm, eval)."""
+
+    def __init__(self, channels, num_heads, patch_size, mlp_ratio, qkv_bias, qk_scale, order_index, T_dim=-1):
+        super().__init__()
+        self.T_dim = T_dim
+        self.cpe = Seq(SubMConv3d(channels, channels, 3, bias=True), nn.Linear(channels, channels), nn.LayerNorm(channels))
+        self.norm1 = Seq(nn.LayerNorm(channels))
+        self.attn = SerializedAttention(channels, num_heads, patch_size, qkv_bias, qk_scale, order_index)
+        self.norm2 = Seq(nn.LayerNorm(channels))
+        self.mlp = Seq(MLP(channels, int(channels * mlp_ratio)))
+        self.drop_path = Seq(nn.Identity())          # DropPath is the identity in eval; no parameters
+        if T_dim != -1:
+            self.t_mlp = nn.Linear(T_dim, channels)
+
+    def forward(self, point, exact):
+        level = point["_level"]
+        x = point["feat"]
+        conv_in = point.pop("conv_in", x)             # stale sparse_conv_feat quirk, see SerializedUnpooling
+        y = self.cpe[0](conv_in, level)
+        y = self.cpe[1](y)
+        _, y = ops.add_layernorm(y, gamma=self.cpe[2].weight, beta=self.cpe[2].bias, eps=self.cpe[2].eps, want_sum=False)
+        t = tb = None
+        if self.T_dim != -1 and "t_scene" in point:    # per-scene timestep rows, broadcast by batch id
+            t = ops.small_linear(point["t_scene"], self.t_mlp.weight, self.t_mlp.bias)
+            tb = level.batch[: level.n]
+        elif self.T_dim != -1 and "t_emb" in point:    # general (per-point) path
+            y = y + self.t_mlp(point["t_emb"])
+        n1 = self.norm1[0]
+        x1, h = ops.add_layernorm(x, y, t, tb, n1.weight, n1.bias, n1.eps)
+        a = self.attn(h, level, exact)
+        n2 = self.norm2[0]
+        x2, h = ops.add_layernorm(x1, a, gamma=n2.weight, beta=n2.bias, eps=n2.eps)
+        point["feat"] = x2 + self.mlp[0](h)
+        return point
+
+
+class SerializedPooling(nn.Module):
+    """ptv3.py:431-555.  The structural half ran in the Plan; here: proj -> segment max -> BN -> GELU."""
+
+    def __init__(self, cin, cout, stride, T_dim=-1):
+        super().__init__()
+        self.stride, self.T_dim = stride, T_dim
+        self.proj = nn.Linear(cin, cout)
+        self.norm = Seq(_bn(cout))
+        self.act = Seq(nn.GELU())
+
+    def forward(self, point, child_level):
+        par = point["_level"]
+        scale, shift = bn_fold(self.norm[0])
+        p = self.proj(point["feat"])
+        feat, coord = ops.pool_reduce(p, point["coord"], child_level.members(), child_level.idx_ptr, child_level.n,
+                                      scale, shift, True)
+        new = Point(feat=feat, coord=coord, _level=child_level, pooling_parent=point,
+                    pooling_inverse=child_level.cluster[: par.n])
+        if "t_scene" in point:
+            new["t_scene"] = point["t_scene"]
+        elif "t_emb" in point and self.T_dim != -1:
+            new["t_emb"] = point["t_emb"][child_level.head[: child_level.n].long()]
+        return new
+
+
+class SerializedUnpooling(nn.Module):
+    """ptv3.py:558-630 incl. the skip-scaling quirks."""
+
+    def __init__(self, cin, cskip, cout, skip_connection_mode="add", skip_connection_scale=False,
+                 skip_connection_scale_i=False, b=1.0, s=1.0):
+        super().__init__()
+        if b != 1.0 or s != 1.0:
+            raise NotImplementedError("FreeU b/s factors != 1 are dead code for every shipped config (ptv3.py:42-100)")
+        self.mode = skip_connection_mode
+        self.proj = Seq(nn.Linear(cin, cout), _bn(cout), nn.GELU())
+        self.proj_skip = Seq(nn.Linear(cskip, cout), _bn(cout), nn.GELU())
+        if skip_connection_mode == "cat":
+            self.proj_cat = Seq(nn.Linear(cout * 2, cout))
+        alpha = 1.0
+        if skip_connection_scale:
+            alpha *= 2 ** (-0.5)                                  # universal_scalling, ptv3.py:34-35
+        if skip_connection_scale_i is not None:
+            alpha *= 0.8 ** (skip_connection_scale_i - 1)         # False -> 0.8**-1 = 1.25 (ptv3.py:610-611)
+        self.alpha = alpha
+        self.cout = cout
+
+    def forward(self, point):
+        parent = point.pop("pooling_parent")
+        cluster = point.pop("pooling_inverse")
+        s1, h1 = bn_fold(self.proj[1])
+        s2, h2 = bn_fold(self.proj_skip[1])
+        up = ops.scale_shift_act(self.proj[0](point["feat"]), s1, h1, 1)
+        skip = ops.scale_shift_act(self.proj_skip[0](parent["feat"]), s2, h2, 1)
+        # reference quirk: parent.feat is assigned directly below (ptv3.py:608-625), so
+        # parent.sparse_conv_feat -- what the next block's CPE conv reads -- keeps `skip`.
+        parent["conv_in"] = skip
+        if self.mode == "add":
+            parent["feat"] = ops.unpool_add(skip, up, cluster, self.alpha)
+        else:
+            w = self.proj_cat[0].weight
+            a = F.linear(skip, w[:, : self.cout])
+            bb = F.linear(up, w[:, self.cout:], self.proj_cat[0].bias)
+            parent["feat"] = ops.unpool_add(a, bb, cluster, self.alpha)
+        return parent
+
+
+class Embedding(nn.Module):
+    """ptv3.py:633-663: SubMConv3d(k=5, bias=False) + BatchNorm + GELU, fused into one kernel."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.stem = Seq(conv=SubMConv3d(cin, cout, 5, bias=False), norm=_bn(cout), act=nn.GELU())
+
+    def forward(self, point):
+        level = point["_level"]
+        scale, shift = bn_fold(self.stem.norm)
+        conv = self.stem.conv
+        if conv.cin <= 8:
+            point["feat"] = conv(point["feat"], level, scale, shift, True)
+        else:
+            point["feat"] = ops.scale_shift_act(conv(point["feat"], level), scale, shift, 1)
+        return point
+
+
+class SerializedCrossAttention(nn.Module):
+    """ptv3.py:859-1055; kv rows are gathered with q's padding map (ptv3.py:1008-1010)."""
+
+    def __init__(self, q_channels, kv_channels, num_heads, q_patch_size, qkv_bias=True, qk_scale=None, order_index=0):
+        super().__init__()
+        if q_channels // num_heads != 16:
+            raise NotImplementedError("head_dim must be 16")
+        self.C, self.H, self.K = q_channels, num_heads, q_patch_size
+        self.scale = qk_scale or (q_channels // num_heads) ** -0.5
+        self.order_index = order_index
+        self.q = nn.Linear(q_channels, q_channels, bias=qkv_bias)
+        self.kv = nn.Linear(kv_channels, q_channels * 2, bias=qkv_bias)
+        self.proj = nn.Linear(q_channels, q_channels)
+
+    def forward(self, xq, q_level, xkv, kv_level, exact):
+        pm = q_level.patch_maps(self.order_index, self.K)
+        if q_level.n != kv_level.n:
+            raise ValueError("TransferModule needs equally sized q / kv levels (ptv3.py:1008-1010)")
+        kv_row = kv_level.order[kv_level.rowmap[self.order_index]][: kv_level.n]
+        pm_kv = ops.patch_maps(kv_row, q_level.scene_count(), pm["K"])
+        (q,) = ops.attn_pack(self.q(xq), 0, self.C, 1, pm, self.H, exact)
+        k, v = ops.attn_pack(self.kv(xkv), 0, self.C, 2, pm_kv, self.H, exact)
+        o = ops.attn(q, k, v, pm, self.H, self.scale, xq.shape[0], exact)
+        return self.proj(o)
+
+
+class CrossBlock(nn.Module):
+    """ptv3.py:1058-1223 with pre_norm=True, tm_feat a float, tm_restomer=False."""
+
+    def __init__(self, q_channels, kv_channels, num_heads, q_patch_size, mlp_ratio, qkv_bias, qk_scale, tm_feat=1.0,
+                 tm_restomer=False):
+        super().__init__()
+        if tm_restomer or not isinstance(tm_feat, (int, float)):
+            raise NotImplementedError("only tm_feat=<float>, tm_restomer=False (all shipped configs) is implemented")
+        self.tm_feat = float(tm_feat)
+        self.q_cpe = Seq(SubMConv3d(q_channels, q_channels, 3), nn.Linear(q_channels, q_channels), nn.LayerNorm(q_channels))
+        self.kv_cpe = Seq(SubMConv3d(kv_channels, kv_channels, 3), nn.Linear(kv_channels, kv_channels),
+                          nn.LayerNorm(kv_channels))
+        self.q_norm1 = Seq(nn.LayerNorm(q_channels))
+        self.kv_norm1 = Seq(nn.LayerNorm(kv_channels))
+        self.attn = SerializedCrossAttention(q_channels, kv_channels, num_heads, q_patch_size, qkv_bias, qk_scale, 0)
+        self.q_norm2 = Seq(nn.LayerNorm(q_channels))
+        self.mlp = Seq(MLP(q_channels, int(q_channels * mlp_ratio)))
+        self.drop_path = Seq(nn.Identity())
+
+    @staticmethod
+    def _cpe(seq, x, level):
+        y = seq[1](seq[0](x, level))
+        return ops.add_layernorm(y, gamma=seq[2].weight, beta=seq[2].bias, eps=seq[2].eps, want_sum=False)[1]
+
+    def forward(self, q_point, kv_point, exact):
+        ql, kl = q_point["_level"], kv_point["_level"]
+        xq, xkv = q_point["feat"], kv_point["feat"]
+        n1, k1, n2 = self.q_norm1[0], self.kv_norm1[0], self.q_norm2[0]
+        q1, hq = ops.add_layernorm(xq, self._cpe(self.q_cpe, xq, ql), gamma=n1.weight, beta=n1.bias, eps=n1.eps)
+        _, hkv = ops.add_layernorm(xkv, self._cpe(self.kv_cpe, xkv, kl), gamma=k1.weight, beta=k1.bias, eps=k1.eps,
+                                   want_sum=False)
+        kv_point["feat"] = hkv                      # the reference leaves LN(kv) in kv_point.feat (ptv3.py:1190-1192)
+        a = self.attn(hq, ql, hkv, kl, exact)
+        if self.tm_feat != 1.0:
+            a = a * self.tm_feat
+        q2, h = ops.add_layernorm(q1, a, gamma=n2.weight, beta=n2.bias, eps=n2.eps)
+        q_point["feat"] = q2 + self.mlp[0](h)
+        return q_point
+
+
+class TransferModule(nn.Module):
+    def __init__(self, **kw):
+        super().__init__()
+        if kw.pop("tm_bidirectional", False):
+            raise NotImplementedError("tm_bidirectional=True is not used by any shipped config")
+        self.cross_block2 = CrossBlock(**kw)
+
+    def forward(self, c_point, n_point, exact):
+        return c_point, self.cross_block2(n_point, c_point, exact)
+
+
+class PointTransformerV3(nn.Module):
+    """Drop-in for the reference class registered as "PT-v3m1" (ptv3.py:1340-1401 ctor kwargs)."""
+
+    def __init__(self, c_in_channels=6, n_in_channels=6, order=("z", "z_trans"),
+                 c_stride=(4, 4), c_enc_depths=(2, 2, 2), c_enc_channels=(32, 64, 128), c_enc_num_head=(2, 4, 8),
+                 c_enc_patch_size=(1024, 1024, 1024), c_dec_depths=(2, 2), c_dec_channels=(64, 64),
+                 c_dec_num_head=(4, 4), c_dec_patch_size=(1024, 1024),
+                 n_stride=(2, 2, 2, 2), n_enc_depths=(2, 2, 2, 6, 2), n_enc_channels=(32, 64, 128, 256, 512),
+                 n_enc_num_head=(2, 4, 8, 16, 32), n_enc_patch_size=(48, 48, 48, 48, 48), n_dec_depths=(2, 2, 2, 2),
+                 n_dec_channels=(64, 64, 128, 256), n_dec_num_head=(4, 4, 8, 16), n_dec_patch_size=(48, 48, 48, 48),
+                 mlp_ratio=4, qkv_bias=True, qk_scale=None, attn_drop=0.0, proj_drop=0.0, drop_path=0.3, pre_norm=True,
+                 shuffle_orders=True, enable_rpe=False, enable_flash=True, upcast_attention=True, upcast_softmax=True,
+                 cls_mode=False, pdnorm_bn=False, pdnorm_ln=False, pdnorm_decouple=True, pdnorm_adaptive=False,
+                 pdnorm_affine=True, pdnorm_conditions=("ScanNet", "S3DIS", "Structured3D"),
+                 num_classes=20, T_dim=128, tm_bidirectional=False, tm_feat=1.0, tm_restomer=False, condition=False,
+                 skip_connection_mode="add", b_factor=(1.0, 1.0, 1.0, 1.0), s_factor=(1.0, 1.0, 1.0, 1.0),
+                 skip_connection_scale=False, skip_connection_scale_i=False):
+        super().__init__()
+        if enable_rpe or pdnorm_bn or pdnorm_ln or cls_mode or not pre_norm:
+            raise NotImplementedError("enable_rpe / pdnorm / cls_mode / post-norm are not used by CDSegNet configs")
+        if attn_drop or proj_drop:
+            raise NotImplementedError("attention / projection dropout is 0 in every shipped config")
+        self.order = [order] if isinstance(order, str) else list(order)
+        self.shuffle_orders = shuffle_orders
+        self.condition = condition
+        self.T_dim = T_dim
+        self.num_classes = num_classes
+        # enable_flash=True -> fp16 tensor-core attention (the reference's flash branch);
+        # enable_flash=False -> exact fp32 attention (the reference's dense branch)
+        self.exact_attention = not enable_flash
+        self.n_cfg = dict(stride=n_stride, enc_depths=n_enc_depths, dec_depths=n_dec_depths)
+        self.c_cfg = dict(stride=c_stride, enc_depths=c_enc_depths, dec_depths=c_dec_depths)
+        no = len(self.order)
+
+        def build(prefix, in_ch, stride, enc_depths, enc_ch, enc_head, enc_patch, dec_depths, dec_ch, dec_head,
+                  dec_patch, T, nn_side):
+            emb = Embedding(in_ch, enc_ch[0])
+            enc = Seq()
+            for s in range(len(enc_depths)):
+                st = Seq()
+                if s > 0:
+                    st.add(SerializedPooling(enc_ch[s - 1], enc_ch[s], stride[s - 1], T_dim=T), name="down")
+                for i in range(enc_depths[s]):
+                    st.add(Block(enc_ch[s], enc_head[s], enc_patch[s], mlp_ratio, qkv_bias, qk_scale, i % no, T_dim=T),
+                           name=f"block{i}")
+                enc.add(st, name=f"enc{s}")
+            dec = Seq()
+            dch = list(dec_ch) + [enc_ch[-1]]
+            for s in reversed(range(len(enc_depths) - 1)):
+                st = Seq()
+                if nn_side:       # ptv3.py:1666-1674
+                    up = SerializedUnpooling(dch[s + 1], enc_ch[s], dch[s],
+                                             skip_connection_mode="add" if skip_connection_mode == "add" else "cat",
+                                             skip_connection_scale=skip_connection_scale)
+                else:             # ptv3.py:1521-1533
+                    up = SerializedUnpooling(dch[s + 1], enc_ch[s], dch[s],
+                                             skip_connection_mode="cat" if skip_connection_mode == "cat_all" else "add",
+                                             skip_connection_scale_i=(s + 1) if skip_connection_scale_i else None,
+                                             b=b_factor[s], s=s_factor[s])
+                st.add(up, name="up")
+                for i in range(dec_depths[s]):
+                    st.add(Block(dch[s], dec_head[s], dec_patch[s], mlp_ratio, qkv_bias, qk_scale, i % no, T_dim=T),
+                           name=f"block{i}")
+                dec.add(st, name=f"dec{s}")
+            return emb, enc, dec, dch
+
+        self._n_embedding, self._n_enc, self._n_dec, n_dch = build(
+            "_n", n_in_channels, n_stride, n_enc_depths, n_enc_channels, n_enc_num_head, n_enc_patch_size,
+            n_dec_depths, n_dec_channels, n_dec_num_head, n_dec_patch_size, -1, False)
+        self._n_head = nn.Linear(n_dch[0], num_classes) if num_classes > 0 else nn.Identity()
+        if condition:
+            self._c_embedding, self._c_enc, self._c_dec, c_dch = build(
+                "_c", c_in_channels, c_stride, c_enc_depths, c_enc_channels, c_enc_num_head, c_enc_patch_size,
+                c_dec_depths, c_dec_channels, c_dec_num_head, c_dec_patch_size, T_dim, True)
+            if T_dim != -1:
+                self.fc_t1 = nn.Linear(T_dim, 4 * T_dim)
+                self.fc_t2 = nn.Linear(4 * T_dim, T_dim)
+            self._c_head = nn.Linear(n_dch[0], c_in_channels) if num_classes > 0 else nn.Identity()   # ptv3.py:1706-1710
+            self._tm_dec0 = TransferModule(
+                q_channels=n_dch[-1], kv_channels=c_dch[-1], num_heads=n_enc_num_head[-1],
+                q_patch_size=n_enc_patch_size[-1], mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                tm_feat=tm_feat, tm_restomer=tm_restomer, tm_bidirectional=tm_bidirectional)
+
+    # ------------------------------------------------------------------------------------
+    @staticmethod
+    def _run_stage(stage, point, levels, s, exact):
+        for name, m in stage._modules.items():
+            if name == "down":
+                point = m(point, levels[s])
+            elif name == "up":
+                point = m(point)
+            else:
+                point = m(point, exact)
+        return point
+
+    def _prep(self, d, level):
+        for key in ("coord", "feat"):
+            if not d[key].is_cuda:
+                raise RuntimeError("cdsegnet_b200: inputs must be CUDA tensors (no CPU fallback)")
+        p = Point(d)
+        p["feat"] = p["feat"].float().contiguous()
+        p["coord"] = p["coord"].float().contiguous()
+        p["_level"] = level
+        p["batch"] = level.batch.long()
+        return p
+
+    @torch.no_grad()
+    def forward(self, c_point=None, n_point=None, perm_fn=None):
+        if self.training:
+            raise NotImplementedError("cdsegnet_b200 round 1 implements the inference forward only")
+        exact = self.exact_attention
+        src = n_point
+        flags = None
+        t_emb = None
+        if self.condition and self.T_dim != -1 and "t_emb" in c_point:
+            t_emb = c_point["t_emb"].float().contiguous()
+            flags = torch.zeros(1, dtype=torch.int32, device=t_emb.device)
+        grid, offset = src["grid_coord"], src["offset"]
+        if flags is not None and t_emb.shape[0] != offset.numel():
+            ops.rows_uniform_flag(t_emb, ops.offset2batch(offset.long().contiguous(), t_emb.shape[0]),
+                                  offset.long().contiguous(), flags)
+        plan = Plan(grid, offset, self.order, self.n_cfg["stride"], self.c_cfg["stride"] if self.condition else None,
+                    self.shuffle_orders, perm_fn, flags)
+        self.last_plan = plan
+        nl = plan.n_levels
+        n = self._prep(n_point, nl[0])
+        n = self._n_embedding(n)
+        if not self.condition:
+            for s in range(len(nl)):
+                n = self._run_stage(self._n_enc[s], n, nl, s, exact)
+            for j in range(len(nl) - 1):
+                n = self._run_stage(self._n_dec[j], n, nl, None, exact)
+            n["feat"] = self._n_head(n["feat"]).contiguous()
+            return self._export(n)
+
+        cl = plan.c_levels
+        c = self._prep(c_point, cl[0])
+        if t_emb is not None:
+            B = offset.numel()
+            if t_emb.shape[0] == B and B != c["feat"].shape[0]:
+                ts = t_emb                                              # already one row per scene
+            elif plan.flags is not None and int(plan.flags[0]) == 0:
+                first = torch.cat([offset.new_zeros(1), offset[:-1]]).long()
+                ts = t_emb.index_select(0, first).contiguous()           # rows are identical inside a scene
+            else:
+                ts = None
+            if ts is not None:                                          # timestep MLP once per scene (ptv3.py:1772-1778)
+                ts = ops.small_linear(ts, self.fc_t1.weight, self.fc_t1.bias, act=2)
+                c["t_scene"] = ops.small_linear(ts, self.fc_t2.weight, self.fc_t2.bias, act=2)
+                c.pop("t_emb", None)
+            else:                                                       # general per-point path
+                t = self.fc_t1(t_emb); t = t * torch.sigmoid(t)
+                t = self.fc_t2(t); c["t_emb"] = t * torch.sigmoid(t)
+        c = self._c_embedding(c)
+        c = self._run_stage(self._c_enc[0], c, cl, 0, exact); n = self._run_stage(self._n_enc[0], n, nl, 0, exact)
+        c = self._run_stage(self._c_enc[1], c, cl, 1, exact); n = self._run_stage(self._n_enc[1], n, nl, 1, exact)
+        n = self._run_stage(self._n_enc[2], n, nl, 2, exact)
+        c = self._run_stage(self._c_enc[2], c, cl, 2, exact); n = self._run_stage(self._n_enc[3], n, nl, 3, exact)
+        n = self._run_stage(self._n_enc[4], n, nl, 4, exact)
+        c, n = self._tm_dec0(c, n, exact)
+        c = self._run_stage(self._c_dec[0], c, cl, None, exact)
+        n = self._run_stage(self._n_dec[0], n, nl, None, exact); n = self._run_stage(self._n_dec[1], n, nl, None, exact)
+        c = self._run_stage(self._c_dec[1], c, cl, None, exact)
+        n = self._run_stage(self._n_dec[2], n, nl, None, exact); n = self._run_stage(self._n_dec[3], n, nl, None, exact)
+        c["feat"] = self._c_head(c["feat"]).contiguous()
+        n["feat"] = self._n_head(n["feat"]).contiguous()
+        return self._export(c), self._export(n)
+
+    @staticmethod
+    def _export(p):
+        """attach the reference-shaped serialization views callers may read"""
+        L = p["_level"]
+        p["serialized_depth"] = L.depth
+        p["serialized_code"] = L.serialized("code")
+        p["serialized_order"] = L.serialized("order")
+        p["serialized_inverse"] = L.serialized("inverse")
+        return p

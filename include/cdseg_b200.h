@@ -1,0 +1,118 @@
+/*
+ * cdseg_b200 -- C ABI of the B200 (sm_100a) kernels behind the CDSegNet PTv3 single-step forward.
+ *
+ * Conventions (mirroring the reference's own native boundary, libs/pointops/src/ * / *_kernel.h,
+ * e.g. libs/pointops/src/knn_query/knn_query_cuda_kernel.h:9-17: C linkage, raw device pointers,
+ * caller allocates every output) with two additions the reference lacks: an explicit
+ * cudaStream_t (passed as void*) and an int status return:
+ *     0  ok        >0  cudaError_t of the failed launch
+ *    -1  invalid argument (shape / alignment / unsupported size)      -2  workspace too small
+ * No entry point allocates, synchronises, or touches the host unless stated.  All pointers are
+ * device pointers unless the comment says "host".  "ptv3.py" below abbreviates
+ * pointcept/models/point_transformer_v3/point_transformer_v3m1_base.py of the reference.
+ */
+#ifndef CDSEG_B200_H
+#define CDSEG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int cdseg_abi_version(void);
+/* number of kernels launched through this library since the last reset (bench.py "gpu_launches") */
+unsigned long long cdseg_launch_count(void);
+void cdseg_launch_count_reset(void);
+
+/* ---- serialization: replaces Point.serialization, pointcept/models/utils/structure.py:47-102 ------------ */
+
+/* max over grid_coord (-> serialized_depth = bit_length(max), structure.py:66).  out_max: int32[1] */
+int cdseg_grid_max(const int32_t* grid, int64_t n_elems, int32_t* out_max, void* stream);
+/* batch[i] = scene of point i from cumulative offsets (pointcept/models/utils/misc.py:19-24) */
+int cdseg_offset2batch(const int64_t* offset, int B, int64_t N, int32_t* batch, void* stream);
+/* codes[r][i] = batch<<3*depth | curve_r(grid[i]) for r < k.  order_ids (host): 0 "z", 1 "z-trans",
+ * 2 "hilbert", 3 "hilbert-trans" (serialization/default.py:9-24; z_order.py:66-101; hilbert.py:91-198) */
+int cdseg_encode_codes(const int32_t* grid, const int32_t* batch, int64_t N, int depth, const int* order_ids,
+                       int k, int64_t* codes, void* stream);
+/* host evaluation of the same bit routines (CPU test-suite only, never on the product path) */
+int cdseg_debug_encode_host(const int32_t* grid, const int32_t* batch, int64_t N, int depth, int order_id,
+                            int64_t* codes);
+/* order = argsort(codes) per row, inverse[order[i]] = i (structure.py:83-92).  nbits = significant key bits. */
+size_t cdseg_argsort_workspace_bytes(int k, int64_t N);
+int cdseg_argsort_rows(const int64_t* codes, int k, int64_t N, int nbits, int32_t* order, int32_t* inverse,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- patch maps: replaces SerializedAttention.get_padding_and_inverse, ptv3.py:188-244 ----------------- */
+/* scene_count: host int64[B] points per scene (B <= 64).  K = patch size, Kp = round_up(K,128) slots per patch.
+ * slot_src/slot_dst: int32[T*Kp], point_slot: int32[N], patch_len: int32[T]  (T from cdseg_patch_count) */
+int cdseg_patch_count(const int64_t* scene_count, int B, int K, int* T_out);
+int cdseg_patch_maps(const int32_t* order, const int64_t* scene_count, int B, int K, int Kp, int32_t* slot_src,
+                     int32_t* slot_dst, int32_t* point_slot, int32_t* patch_len, void* stream);
+
+/* ---- grid pooling: replaces SerializedPooling, ptv3.py:464-531 and unpool gather, ptv3.py:623 ---------- */
+/* One pooling level, sync-free.  Parent: code int64[k][ld], order int32[k][ld], grid int32[n,3], batch int32[n];
+ * n = *n_dev if n_dev != NULL (count produced on the device by the previous level) else n_host.
+ * c0 = curve whose codes define the clusters (logical row 0 after the reference's shuffle).
+ * Outputs: cluster int32[n] (= pooling_inverse), idx_ptr int32[m+1], head int32[m], child code/order/inverse
+ * with row stride ld_c, child grid/batch, *m_dev = m, c_offset int64[B] cumulative child offsets. */
+size_t cdseg_pool_plan_workspace_bytes(int k, int64_t ld);
+int cdseg_pool_plan(const int64_t* code, const int32_t* order, int k, int64_t ld, const int32_t* n_dev,
+                    int64_t n_host, int c0, int pooling_depth, const int32_t* grid, const int32_t* batch,
+                    int32_t* cluster, int32_t* idx_ptr, int32_t* head, int64_t* c_code, int32_t* c_order,
+                    int32_t* c_inverse, int64_t ld_c, int32_t* c_grid, int32_t* c_batch, int32_t* m_dev,
+                    int64_t* c_offset, void* workspace, size_t workspace_bytes, void* stream);
+/* out[j] = act(bn(max_{i in cluster j} x[i])) ; out_coord[j] = mean coord (torch_scatter.segment_csr, ptv3.py:507-531)
+ * members = parent order of curve c0 (cluster members are contiguous there), idx_ptr from the plan */
+int cdseg_pool_reduce(const float* x, const float* coord, const int32_t* members, const int32_t* idx_ptr, int64_t m,
+                      int C, const float* bn_scale, const float* bn_shift, int gelu, float* out, float* out_coord,
+                      void* stream);
+/* out[i] = a[i]*alpha + b[cluster[i]]   (ptv3.py:608-623) */
+int cdseg_unpool_add(const float* a, const float* b, const int32_t* cluster, int64_t n, int C, float alpha,
+                     float* out, void* stream);
+
+/* ---- submanifold conv: replaces spconv.SubMConv3d at ptv3.py:356-362, 647-654, 1106-1123 ---------------- */
+size_t cdseg_nbr_workspace_bytes(int64_t n);
+int64_t cdseg_hash_capacity(int64_t n);
+/* nbr int32[n, ksize^3]: index of the active voxel at grid[i] + (a-r, b-r, c-r), tap t = (a*ks+b)*ks+c, or -1 */
+int cdseg_nbr_build(const int32_t* grid, const int32_t* batch, int64_t n, int ksize, int32_t* nbr, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* out[n,Co] = bias + sum_t in[nbr[:,t]] @ wt[t]; wt fp32 [ksize^3][Ci][Co]; optional folded BN + GELU epilogue
+ * (only for Ci <= 8, the Embedding stem) */
+int cdseg_subm_conv(const float* in, const int32_t* nbr, const float* wt, const float* bias, const float* ep_scale,
+                    const float* ep_shift, int ep_gelu, int64_t n, int Ci, int Co, int ksize, float* out,
+                    void* stream);
+
+/* ---- serialized patch attention: replaces flash_attn varlen calls at ptv3.py:282-289, 1038-1047 -------- */
+/* gather rows by slot_src into per-(head,patch) tiles [H][T][Kp][16]; src fp32 [n, ld]; tensor w in [0,nwhich)
+ * takes columns col0 + w*C + h*16 ...  (ptv3.py:258-262 "qkv[order]") */
+int cdseg_attn_pack_f16(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src, int H,
+                        int T, int Kp, void* dst0, void* dst1, void* dst2, void* stream);
+int cdseg_attn_pack_f32(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src, int H,
+                        int T, int Kp, float* dst0, float* dst1, float* dst2, void* stream);
+/* tcgen05/TMEM kernel: fp16 operands, fp32 accumulate; out fp32 [n, out_ld] rows scattered by slot_dst (":290 feat[inverse]") */
+size_t cdseg_attn_tc_smem_bytes(int Kp);
+int cdseg_attn_tc(const void* Q, const void* K, const void* V, const int32_t* patch_len, const int32_t* slot_dst,
+                  int H, int T, int Kp, float scale, float* out, int64_t out_ld, void* stream);
+/* exact fp32 SIMT kernel (dense-branch numerics, ptv3.py:264-280) */
+int cdseg_attn_exact(const float* Q, const float* K, const float* V, const int32_t* patch_len,
+                     const int32_t* slot_dst, int H, int T, int Kp, float scale, float* out, int64_t out_ld,
+                     void* stream);
+
+/* ---- row-wise fused ops: ptv3.py:402-424 (residual + t_mlp + LayerNorm), 549-553/575-593 (BN+GELU), 1772-1778 */
+/* y = a (+ b) (+ t[batch]) ; y_out = y (nullable) ; ln_out = LayerNorm(y) (nullable) */
+int cdseg_add_layernorm(const float* a, const float* b, const float* t, const int32_t* batch, const float* gamma,
+                        const float* beta, float eps, int64_t n, int C, float* y_out, float* ln_out, void* stream);
+/* out = act(x*scale[c] + shift[c]); act 0 none, 1 GELU(erf) */
+int cdseg_scale_shift_act(const float* x, const float* scale, const float* shift, int act, int64_t n, int C,
+                          float* out, void* stream);
+/* out[r][o] = act(bias[o] + x[r].W[o]) for a handful of rows (per-scene timestep MLP); act 0 none, 2 swish */
+int cdseg_small_linear(const float* x, const float* W, const float* bias, int act, int R, int K, int O, float* out,
+                       void* stream);
+/* flag[0] |= 1 if any row of x differs from the first row of its scene */
+int cdseg_rows_uniform(const float* x, const int32_t* batch, const int64_t* offset, int64_t n, int C, int32_t* flag,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,252 @@
+"""GPU parity suite (-m gpu): every C-ABI kernel against the CPU oracle on the same seeded inputs.
+Integer / index work is compared bit-exactly; floating point with the tolerance stated in the test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import serialization_np as S
+from oracle import ptv3_oracle as O
+
+pytestmark = pytest.mark.gpu
+ORDERS = ("z", "z-trans", "hilbert", "hilbert-trans")
+DEV = "cuda"
+
+
+def cu(a, dtype=None):
+    x = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return x.to(dtype) if dtype is not None else x
+
+
+@pytest.fixture(scope="module")
+def ops(lib):
+    from cdsegnet_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("depth", (1, 3, 9, 11, 16))
+def test_encode_bit_exact(ops, depth):
+    z = np.load(os.path.join(GOLDEN, "codes.npz"))
+    g, b = cu(z[f"grid_{depth}"], torch.int32), cu(z[f"batch_{depth}"], torch.int32)
+    codes = ops.encode_codes(g, b, depth, ORDERS).cpu().numpy()
+    for r, o in enumerate(ORDERS):
+        assert np.array_equal(codes[r], z[f"code_{depth}_{o}"]), (depth, o)
+    assert int(ops.grid_max(g).item()) == int(z[f"grid_{depth}"].max())
+
+
+@pytest.mark.parametrize("n,bits", [(1, 5), (31, 9), (4096, 27), (4097, 30), (120000, 27), (300000, 40), (70000, 51)])
+def test_argsort_bit_exact(ops, n, bits):
+    rng = np.random.default_rng(n)
+    codes = rng.integers(0, 1 << bits, size=(4, n), dtype=np.int64)
+    codes[1] = rng.integers(0, 7, size=n)            # heavy duplicates -> exercises stability
+    order, inverse = ops.argsort_rows(cu(codes), bits)
+    order, inverse = order.cpu().numpy(), inverse.cpu().numpy()
+    ref = np.argsort(codes, axis=1, kind="stable")
+    assert np.array_equal(order, ref)
+    for r in range(4):
+        assert np.array_equal(inverse[r][order[r]], np.arange(n))
+
+
+def test_argsort_empty_and_zero_bits(ops):
+    o, i = ops.argsort_rows(torch.zeros((4, 0), dtype=torch.int64, device=DEV), 10)
+    assert o.shape == (4, 0)
+    o, i = ops.argsort_rows(torch.zeros((2, 100), dtype=torch.int64, device=DEV), 0)
+    assert np.array_equal(o.cpu().numpy()[0], np.arange(100))
+
+
+def _scene(counts, seed=0):
+    from cdsegnet_b200 import synth
+    return synth.collate([synth.small_room(c, seed + i) for i, c in enumerate(counts)])
+
+
+@pytest.mark.parametrize("counts", [(2000,), (1500, 700, 1100)])
+def test_plan_vs_oracle(ops, counts):
+    """serialization + the whole pooling hierarchy (CN strides 2,2,2,2 / NN strides 4,4) bit-exact,
+    including the reference's shuffle bookkeeping"""
+    from cdsegnet_b200.structure import Plan
+    sc = _scene(counts)
+    rng = np.random.default_rng(7)
+    perms = [rng.permutation(4) for _ in range(8)]
+    it = iter(perms)
+    plan = Plan(cu(sc["grid_coord"]), cu(sc["offset"]), ORDERS, (2, 2, 2, 2), (4, 4), True, lambda k: next(it))
+    batch = S.offset2batch(sc["offset"])
+    code, order, inverse, depth = S.serialization(sc["grid_coord"], batch)
+    pi = iter(perms)
+
+    def shuffle(c, o, i):
+        p = next(pi)
+        return c[p], o[p], i[p]
+    c0 = shuffle(code, order, inverse)
+    n0 = shuffle(code, order, inverse)
+
+    def check(L, c, o, i, d):
+        assert L.depth == d and L.n == c.shape[1]
+        assert np.array_equal(L.serialized("code").cpu().numpy(), c)
+        assert np.array_equal(L.serialized("order").cpu().numpy(), o)
+        assert np.array_equal(L.serialized("inverse").cpu().numpy(), i)
+
+    check(plan.c_levels[0], *c0, depth)
+    check(plan.n_levels[0], *n0, depth)
+    state = {"c": (c0, depth, sc["grid_coord"], batch), "n": (n0, depth, sc["grid_coord"], batch)}
+    sched = [("c", 1, 4), ("n", 1, 2), ("n", 2, 2), ("c", 2, 4), ("n", 3, 2), ("n", 4, 2)]
+    for net, li, stride in sched:
+        (c, o, i), d, g, b = state[net]
+        pl = S.pool_plan(c, stride, d)
+        cc, oo, ii = shuffle(pl["code"], pl["order"], pl["inverse"])
+        L = (plan.c_levels if net == "c" else plan.n_levels)[li]
+        check(L, cc, oo, ii, pl["depth"])
+        par_n = c.shape[1]
+        assert np.array_equal(L.cluster[:par_n].cpu().numpy(), pl["cluster"])            # pooling_inverse
+        assert np.array_equal(L.idx_ptr[: L.n + 1].cpu().numpy(), pl["idx_ptr"])
+        head = L.head[: L.n].cpu().numpy()
+        assert np.array_equal(pl["cluster"][head], np.arange(L.n))                       # any member is a valid head
+        members = L.members().cpu().numpy()
+        assert np.array_equal(pl["cluster"][members], np.repeat(np.arange(L.n), pl["counts"]))
+        g2 = g[pl["head_indices"]] >> pl["pooling_depth"]
+        b2 = b[pl["head_indices"]]
+        assert np.array_equal(L.grid[: L.n].cpu().numpy(), g2) and np.array_equal(L.batch[: L.n].cpu().numpy(), b2)
+        assert np.array_equal(L.offset_host, np.cumsum(np.bincount(b2, minlength=len(counts))))
+        state[net] = ((cc, oo, ii), pl["depth"], g2, b2)
+
+
+@pytest.mark.parametrize("counts,K", [((5, 12), 4), ((10,), 4), ((3, 11), 4), ((1024, 3000, 3001), 1024), ((130,), 128),
+                                      ((127, 300), 128)])
+def test_patch_maps_vs_reference_padding(ops, counts, K):
+    n = sum(counts)
+    order = np.random.default_rng(0).permutation(n).astype(np.int32)
+    pm = ops.patch_maps(cu(order), np.array(counts), K)
+    pad, unpad, cu_seq = S.patch_maps(np.cumsum(counts), K)
+    src, dst, ps, plen = (pm[k].cpu().numpy() for k in ("slot_src", "slot_dst", "point_slot", "patch_len"))
+    Kp, T = pm["Kp"], pm["T"]
+    assert T == len(cu_seq) - 1 and np.array_equal(plen, np.diff(cu_seq))
+    # packed slot t*Kp + j  <->  reference padded slot cu[t] + j
+    ref_slot = np.concatenate([cu_seq[t] + np.arange(plen[t]) for t in range(T)])
+    packed = np.concatenate([t * Kp + np.arange(plen[t]) for t in range(T)])
+    assert np.array_equal(src[packed], order[pad[ref_slot]])                # == serialized_order[pad]
+    mask = np.ones(T * Kp, bool); mask[packed] = False
+    assert (src[mask] == -1).all() and (dst[mask] == -1).all()
+    inv = np.empty(n, np.int64); inv[order] = np.arange(n)
+    to_packed = np.empty(int(cu_seq[-1]), np.int64); to_packed[ref_slot] = packed
+    assert np.array_equal(ps, to_packed[unpad[inv]])                        # == unpad[serialized_inverse]
+    real = dst >= 0
+    assert real.sum() == n and np.array_equal(np.sort(dst[real]), np.arange(n))
+    assert np.array_equal(ps[dst[real]], np.nonzero(real)[0])
+
+
+@pytest.mark.parametrize("ks", (3, 5))
+def test_nbr_table(ops, ks):
+    sc = _scene((1800, 900))
+    g, b = sc["grid_coord"], S.offset2batch(sc["offset"])
+    nbr = ops.nbr_build(cu(g), cu(b, torch.int32), ks).cpu().numpy()
+    key = {(int(bb), *map(int, gg)): i for i, (bb, gg) in enumerate(zip(b, g))}
+    r = ks // 2
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, len(g), 300):
+        for t in range(ks ** 3):
+            a, bb, c = t // (ks * ks), (t // ks) % ks, t % ks
+            q = (int(b[i]), int(g[i, 0]) + a - r, int(g[i, 1]) + bb - r, int(g[i, 2]) + c - r)
+            assert nbr[i, t] == key.get(q, -1)
+
+
+@pytest.mark.parametrize("ci,co,ks", [(6, 32, 5), (4, 32, 5), (16, 16, 3), (32, 32, 3), (64, 64, 3), (96, 96, 3), (128, 128, 3)])
+def test_subm_conv_vs_oracle(ops, ci, co, ks):
+    sc = _scene((1500, 600))
+    g, b = sc["grid_coord"], S.offset2batch(sc["offset"])
+    gen = torch.Generator().manual_seed(ci * 100 + co)
+    x = torch.randn(len(g), ci, generator=gen)
+    w = torch.randn(co, ks, ks, ks, ci, generator=gen) / (ks ** 3 * ci * 0.4) ** 0.5
+    bias = torch.randn(co, generator=gen) if ks == 3 else None
+    ref = O.subm_conv3d(x, torch.from_numpy(b), torch.from_numpy(g), w, bias)
+    nbr = ops.nbr_build(cu(g), cu(b, torch.int32), ks)
+    wt = w.reshape(co, ks ** 3, ci).permute(1, 2, 0).contiguous().to(DEV)
+    out = ops.subm_conv(x.to(DEV), nbr, wt, bias.to(DEV) if bias is not None else None, ks).cpu()
+    assert (out - ref).abs().max() < 2e-5          # fp32 accumulate, different summation order only
+
+
+def test_pool_reduce_unpool_rowwise(ops):
+    sc = _scene((2000, 1200))
+    batch = S.offset2batch(sc["offset"])
+    code, order, inverse, depth = S.serialization(sc["grid_coord"], batch)
+    pl = S.pool_plan(code, 2, depth)
+    m, n, C = len(pl["counts"]), len(batch), 48
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(n, C, generator=gen); coord = torch.from_numpy(sc["coord"])
+    scale, shift = torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen)
+    cl = torch.from_numpy(pl["cluster"])
+    ref = torch.nn.functional.gelu(O.segment_max(x, cl, m) * scale + shift)
+    refc = O.segment_mean(coord, cl, torch.from_numpy(pl["counts"]))
+    out, outc = ops.pool_reduce(x.to(DEV), coord.to(DEV), cu(pl["indices"], torch.int32), cu(pl["idx_ptr"], torch.int32),
+                                m, scale.to(DEV), shift.to(DEV), True)
+    assert (out.cpu() - ref).abs().max() < 1e-5 and (outc.cpu() - refc).abs().max() < 1e-5
+    up = torch.randn(m, C, generator=gen)
+    got = ops.unpool_add(x.to(DEV), up.to(DEV), cu(pl["cluster"], torch.int32), 1.25 * 2 ** -0.5).cpu()
+    assert (got - (x * (1.25 * 2 ** -0.5) + up[cl])).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("C", (16, 32, 64, 96, 128, 256, 512))
+def test_add_layernorm(ops, C):
+    gen = torch.Generator().manual_seed(C)
+    n, B = 777, 3
+    a, b = torch.randn(n, C, generator=gen), torch.randn(n, C, generator=gen)
+    tt = torch.randn(B, C, generator=gen); batch = torch.randint(0, B, (n,), generator=gen).sort().values
+    g, be = torch.randn(C, generator=gen), torch.randn(C, generator=gen)
+    y, ln = ops.add_layernorm(a.to(DEV), b.to(DEV), tt.to(DEV), batch.int().to(DEV), g.to(DEV), be.to(DEV), 1e-5)
+    ry = a + b + tt[batch]
+    assert (y.cpu() - ry).abs().max() < 1e-6
+    assert (ln.cpu() - torch.nn.functional.layer_norm(ry, (C,), g, be, 1e-5)).abs().max() < 2e-5
+    _, ln2 = ops.add_layernorm(a.to(DEV), gamma=g.to(DEV), beta=be.to(DEV), want_sum=False)
+    assert (ln2.cpu() - torch.nn.functional.layer_norm(a, (C,), g, be, 1e-5)).abs().max() < 2e-5
+
+
+def test_small_linear_and_scale_shift(ops):
+    gen = torch.Generator().manual_seed(5)
+    x, W, b = torch.randn(3, 128, generator=gen), torch.randn(512, 128, generator=gen) / 11, torch.randn(512, generator=gen)
+    ref = torch.nn.functional.linear(x, W, b); ref = ref * torch.sigmoid(ref)
+    assert (ops.small_linear(x.to(DEV), W.to(DEV), b.to(DEV), act=2).cpu() - ref).abs().max() < 1e-5
+    y = torch.randn(1001, 64, generator=gen); s, h = torch.randn(64, generator=gen), torch.randn(64, generator=gen)
+    got = ops.scale_shift_act(y.to(DEV), s.to(DEV), h.to(DEV), 1).cpu()
+    assert (got - torch.nn.functional.gelu(y * s + h)).abs().max() < 1e-5
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    off = torch.tensor([400, 1001], device=DEV)
+    rows = torch.cat([y[:1].expand(400, -1), y[1:2].expand(601, -1)]).contiguous().to(DEV)
+    ops.rows_uniform_flag(rows, ops.offset2batch(off, 1001), off, flag)
+    assert int(flag.item()) == 0
+    rows[700, 3] += 1
+    ops.rows_uniform_flag(rows, ops.offset2batch(off, 1001), off, flag)
+    assert int(flag.item()) == 1
+
+
+def _attn_case(ops, counts, K, H, exact, seed=0):
+    n, C = sum(counts), H * 16
+    gen = torch.Generator().manual_seed(seed)
+    qkv = torch.randn(n, 3 * C, generator=gen) * 1.5
+    order = torch.randperm(n, generator=gen).numpy()
+    pad, unpad, cu_seq = S.patch_maps(np.cumsum(counts), K)
+    inv = np.empty(n, np.int64); inv[order] = np.arange(n)
+    g = qkv[torch.from_numpy(order[pad])]
+    mode = "dense" if exact else "flash16"
+    ref = O.varlen_attention(g[:, :C], g[:, C:2 * C], g[:, 2 * C:], cu_seq, H, 0.25, mode)[torch.from_numpy(unpad[inv])]
+    pm = ops.patch_maps(cu(order.astype(np.int32)), np.array(counts), K)
+    q, k, v = ops.attn_pack(qkv.to(DEV), 0, C, 3, pm, H, exact)
+    out = ops.attn(q, k, v, pm, H, 0.25, n, exact)
+    torch.cuda.synchronize()
+    return out.cpu(), ref
+
+
+@pytest.mark.parametrize("counts,K,H", [((300,), 128, 2), ((1000, 77, 129), 128, 4), ((64,), 64, 1), ((2500,), 1024, 2),
+                                         ((991,), 1024, 8), ((40, 900), 256, 3)])
+def test_attention_exact_vs_dense_oracle(ops, counts, K, H):
+    out, ref = _attn_case(ops, counts, K, H, exact=True)
+    assert (out - ref).abs().max() < 2e-5          # fp32 both sides
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("counts,K,H", [((128,), 128, 1), ((300,), 128, 2), ((1000, 77, 129), 128, 4), ((64,), 64, 1),
+                                         ((2500,), 1024, 2), ((991,), 1024, 8), ((40, 900), 256, 3), ((5000,), 1024, 4)])
+def test_attention_tcgen05_vs_flash_oracle(ops, counts, K, H):
+    """fp16 operands / fp32 accumulate / fp16 probabilities, like flash_attn: tolerance 2e-3 abs on
+    outputs of magnitude ~1 (fp16 rounding of P and of the reference's fp16 output)"""
+    out, ref = _attn_case(ops, counts, K, H, exact=False)
+    assert (out - ref).abs().max() < 2e-3
