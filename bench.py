@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- points/sec of the CDSegNet single-step forward (BASELINE.json metric) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (CPU oracle port)
+
+A "step" = one full DefaultSegmentorV2.inference(eval=False) of one synthetic ScanNet-shaped scene of
+120 000 unique voxels (BASELINE.json configs[1]) through the full CDSegNet (CN + NN + TransferModule,
+101.4 M parameters): serialization (key encode + 4 radix argsorts), pooling hierarchy, 37 blocks, heads.
+Scenes shard one per GPU (no collective on the inference forward) => weak scaling.
+Prints ONE JSON line on rank 0 (contract in the task statement; fields documented in DESIGN.md §Measurement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 120000
+METRIC = "points/sec (120k-point ScanNet-shaped scene, full CDSegNet single-step forward)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        mx = max((float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def make_scene(seed, n=N_POINTS):
+    from cdsegnet_b200 import synth
+    if n >= 60000:
+        sc = synth.scannet_scene(n, seed)
+    else:   # bounded CPU sample: same generator, smaller room so that surface density stays ScanNet-like
+        f = (n / N_POINTS) ** 0.5
+        sc = synth.scannet_scene(n, seed, room_m=(max(2.0, 8.0 * f), max(1.6, 6.0 * f), 3.0), n_boxes=max(2, int(12 * f)))
+    return synth.collate([sc])
+
+
+def random_weights(model, seed=0):
+    """reference default init under a fixed seed + randomised BN running stats."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+            m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_forward_timed(n_points, seed=0, repeats=1):
+    """the oracle (CPU port of the reference forward, dense fp32 attention) on the host cores."""
+    import numpy as np
+    import torch
+    from oracle import ptv3_oracle as O
+    import cdsegnet_b200 as cb
+    from cdsegnet_b200 import configs
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    cfg = configs.backbone_cfg()
+    torch.manual_seed(0)
+    model = cb.PointTransformerV3(**cfg)
+    random_weights(model)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    sc = make_scene(seed, n_points)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    base = dict(coord=t(sc["coord"]), grid_coord=t(sc["grid_coord"]).long(), offset=t(sc["offset"]))
+    n = len(sc["coord"])
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        noise = torch.normal(0, 1, size=(n, 6))
+        ts = 999 * torch.ones((n, 1), dtype=torch.int64)
+        O.forward(sd, cfg, dict(base, feat=noise, t_emb=O.calc_t_emb(ts, 128)), dict(base, feat=t(sc["feat"])), attn_mode="dense")
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n / best, cores, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    n = args.cpu_points
+    vals = []
+    for _ in range(args.warmup):
+        cpu_forward_timed(n)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, cores, dt = cpu_forward_timed(n)
+        vals.append(dt)
+    total = time.perf_counter() - t0
+    value = n * args.steps / sum(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(vals) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ScanNet-shaped scene, full CDSegNet (CN+NN) fp32 single-step forward, CPU",
+                       "points_per_step": n},
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} forward(s) of a {n}-point scene (bounded sample of the 120k workload)"},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": total}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import cdsegnet_b200 as cb
+    from cdsegnet_b200 import configs, ops
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    seg = cb.build_model(configs.segmentor_cfg())           # enable_flash=True: the shipped config (fp16 tensor-core attention)
+    random_weights(seg)
+    seg = seg.to(dev).eval()
+
+    sc = make_scene(seed=rank)
+    n = len(sc["coord"])
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in sc.items()}
+    host["grid_coord"] = host["grid_coord"].int().pin_memory()
+    resident = {k: v.to(dev) for k, v in host.items()}
+    noise_dev = torch.randn(n, 6, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step_resident():
+        return seg.inference(resident, eval=False, noise=noise_dev)["seg_logits"]
+
+    logits_host = torch.empty((n, 20), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        out = seg.inference(inp, eval=False)["seg_logits"]              # draws the NN noise like default.py:393
+        logits_host.copy_(out, non_blocking=True)
+        return out
+
+    def timed(fn, steps, warmup, profile_attn=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        ops.launch_count_reset()
+        if profile_attn:
+            ops.PROFILE = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()                                                # L2 flush between timed iterations (untimed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        launches = ops.launch_count()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        prof = ops.PROFILE
+        ops.PROFILE = None
+        tsum = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tsum, op=dist.ReduceOp.MAX)
+        return float(tsum.item()), launches, wall, prof
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, launches, wall, prof = timed(step_resident, args.steps, args.warmup, profile_attn=True)
+    clocks = sampler.summary()
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+
+    value = world * n * args.steps / (ms_total / 1e3)
+    e2e = world * n * args.steps / (ms_e2e / 1e3)
+    hbm, tf_burst, tf_sust, which = peaks()
+
+    # dominant kernel: the tcgen05 patch-attention launches of the largest stage (CN/NN stage 0, C=32)
+    roof = None
+    if prof:
+        big = max(p[2] for p in prof)
+        sel = [p for p in prof if p[2] == big]
+        dur = sum(a.elapsed_time(b) for a, b, _, _ in sel) / len(sel)
+        ach = big / (dur * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "tc::attn_tc_kernel (stage 0: %d launches/step)" % (len(sel) // args.steps),
+                "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust, "traffic": None,
+                "peak_source": which + " bf16_tflops_sustained (kernel timed inside the step)",
+                "flops_per_launch": big, "ms_per_launch": dur, "exp_per_launch": sel[0][3],
+                "gexp_per_s": sel[0][3] / (dur * 1e-3) / 1e9}
+
+    line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (dense layers, conv, norms) + f16 tensor-core attention with f32 accumulate (reference flash branch)",
+            "data": "synthetic",
+            "config": {"workload": "ScanNet-shaped scene 120k unique voxels @0.02 m, full CDSegNet (CN+NN+TransferModule, 101.4M params), "
+                                   "single-step inference forward, patch 1024, 1 scene per GPU",
+                       "points_per_step_per_gpu": n, "l2": "flushed (256 MiB write) between timed iterations",
+                       "parallelism": f"scene-per-GPU x{world}, no collective"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e, "unit": "points/s",
+                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) + n * 6 * 4),
+                    "d2h_bytes_per_step": int(n * 20 * 4), "ms_per_step": ms_e2e / args.steps},
+            "roofline": roof}
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            v, cores, dt = cpu_forward_timed(args.cpu_points)
+            line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
+                                    "sample": f"1 forward of a {args.cpu_points}-point scene, same model (bounded sample, {dt:.1f} s)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--cpu-points", type=int, default=40000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -226,9 +226,11 @@ attn_tc_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, co
         if (dst >= 0) {
           const float inv = 1.f / l;
           float4* op = reinterpret_cast<float4*>(out + (int64_t)dst * out_ld + h * 16);
+          // flash_attn returns fp16 and the reference widens it again (ptv3.py:289): same rounding point here
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            op[j] = make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
+            op[j] = make_float4(__half2float(__float2half_rn(acc[4 * j] * inv)), __half2float(__float2half_rn(acc[4 * j + 1] * inv)),
+                                __half2float(__float2half_rn(acc[4 * j + 2] * inv)), __half2float(__float2half_rn(acc[4 * j + 3] * inv)));
         }
 #pragma unroll
         for (int d = 0; d < 16; ++d) acc[d] = 0.f;

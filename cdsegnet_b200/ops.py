@@ -12,6 +12,7 @@ from . import _lib
 from ._lib import check
 
 ORDER_IDS = {"z": 0, "z-trans": 1, "hilbert": 2, "hilbert-trans": 3}
+PROFILE = None     # bench.py sets this to a list to collect (start_event, end_event, flops, exps) per attention launch
 
 
 def _p(t, dtype=None):
@@ -86,7 +87,10 @@ def patch_maps(order_row, scene_count, K):
     patch_len = torch.empty(T, dtype=torch.int32, device=dev)
     check(lib.cdseg_patch_maps(_p(order_row, torch.int32), cnt, B, K, Kp, _p(slot_src), _p(slot_dst), _p(point_slot),
                                _p(patch_len), _stream()), "patch_maps")
-    return dict(slot_src=slot_src, slot_dst=slot_dst, point_slot=point_slot, patch_len=patch_len, T=T, Kp=Kp, K=K)
+    # algorithmic (query, key) pairs of this partition, padding rows excluded
+    pairs = int(sum(int(c) * (K if int(c) > K else int(c)) for c in scene_count))
+    return dict(slot_src=slot_src, slot_dst=slot_dst, point_slot=point_slot, patch_len=patch_len, T=T, Kp=Kp, K=K,
+                pairs=pairs)
 
 
 # ---------------------------------------------------------------- pooling
@@ -179,8 +183,14 @@ def attn(q, k, v, pm, H, scale, n_out, exact=False):
     C = H * 16
     out = torch.empty((n_out, C), dtype=torch.float32, device=q.device)
     fn = lib.cdseg_attn_exact if exact else lib.cdseg_attn_tc
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(fn(_p(q), _p(k), _p(v), _p(pm["patch_len"]), _p(pm["slot_dst"]), H, pm["T"], pm["Kp"], float(scale), _p(out),
              C, _stream()), "attn")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((e0, e1, 4.0 * pm["pairs"] * C, pm["pairs"] * H))
     return out
 
 

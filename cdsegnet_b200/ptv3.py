@@ -362,6 +362,9 @@ class PointTransformerV3(nn.Module):
         # enable_flash=True -> fp16 tensor-core attention (the reference's flash branch);
         # enable_flash=False -> exact fp32 attention (the reference's dense branch)
         self.exact_attention = not enable_flash
+        # evaluate the timestep MLP once per scene when the t_emb rows are uniform inside each scene
+        # (always true for DefaultSegmentorV2: default.py:400-402, 451-454); False forces the per-point path
+        self.t_emb_per_scene = True
         self.n_cfg = dict(stride=n_stride, enc_depths=n_enc_depths, dec_depths=n_dec_depths)
         self.c_cfg = dict(stride=c_stride, enc_depths=c_enc_depths, dec_depths=c_dec_depths)
         no = len(self.order)
@@ -471,9 +474,9 @@ class PointTransformerV3(nn.Module):
         c = self._prep(c_point, cl[0])
         if t_emb is not None:
             B = offset.numel()
-            if t_emb.shape[0] == B and B != c["feat"].shape[0]:
+            if self.t_emb_per_scene and t_emb.shape[0] == B and B != c["feat"].shape[0]:
                 ts = t_emb                                              # already one row per scene
-            elif plan.flags is not None and int(plan.flags[0]) == 0:
+            elif self.t_emb_per_scene and plan.flags is not None and int(plan.flags[0]) == 0:
                 first = torch.cat([offset.new_zeros(1), offset[:-1]]).long()
                 ts = t_emb.index_select(0, first).contiguous()           # rows are identical inside a scene
             else:

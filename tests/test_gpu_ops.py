@@ -250,3 +250,24 @@ def test_attention_tcgen05_vs_flash_oracle(ops, counts, K, H):
     outputs of magnitude ~1 (fp16 rounding of P and of the reference's fp16 output)"""
     out, ref = _attn_case(ops, counts, K, H, exact=False)
     assert (out - ref).abs().max() < 2e-3
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("counts,K,H", [((1000, 77, 129), 128, 4), ((2500,), 1024, 2), ((5000,), 1024, 4)])
+def test_attention_tcgen05_vs_real_flash_attn(ops, counts, K, H):
+    """against the upstream kernel itself (flash_attn is installed on the GPU box): same inputs, same
+    varlen partition; both are fp16-in / fp32-accumulate / fp16-out, so 1e-3 abs"""
+    fa = pytest.importorskip("flash_attn")
+    n, C = sum(counts), H * 16
+    gen = torch.Generator().manual_seed(1)
+    qkv = torch.randn(n, 3 * C, generator=gen) * 1.5
+    order = torch.randperm(n, generator=gen).numpy()
+    pad, unpad, cu_seq = S.patch_maps(np.cumsum(counts), K)
+    inv = np.empty(n, np.int64); inv[order] = np.arange(n)
+    g = qkv[torch.from_numpy(order[pad])].to(DEV)
+    ref = fa.flash_attn_varlen_qkvpacked_func(g.half().reshape(-1, 3, H, 16), cu(cu_seq), max_seqlen=K, dropout_p=0,
+                                              softmax_scale=0.25).reshape(-1, C).float()[cu(unpad[inv])]
+    pm = ops.patch_maps(cu(order.astype(np.int32)), np.array(counts), K)
+    q, k, v = ops.attn_pack(qkv.to(DEV), 0, C, 3, pm, H, False)
+    out = ops.attn(q, k, v, pm, H, 0.25, n, False)
+    assert (out - ref).abs().max().item() < 1e-3
