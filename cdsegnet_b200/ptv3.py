@@ -435,10 +435,12 @@ class PointTransformerV3(nn.Module):
             if not d[key].is_cuda:
                 raise RuntimeError("cdsegnet_b200: inputs must be CUDA tensors (no CPU fallback)")
         p = Point(d)
-        p["feat"] = p["feat"].float().contiguous()
-        p["coord"] = p["coord"].float().contiguous()
+        pl = level.perm.long()                       # caller's numbering -> internal (curve-order) numbering
+        p["feat"] = p["feat"].float()[pl].contiguous()
+        p["coord"] = p["coord"].float()[pl].contiguous()
+        if "t_emb" in p and p["t_emb"].shape[0] == pl.shape[0]:
+            p["t_emb"] = p["t_emb"].float()[pl].contiguous()
         p["_level"] = level
-        p["batch"] = level.batch.long()
         return p
 
     @torch.no_grad()
@@ -486,7 +488,9 @@ class PointTransformerV3(nn.Module):
                 c["t_scene"] = ops.small_linear(ts, self.fc_t2.weight, self.fc_t2.bias, act=2)
                 c.pop("t_emb", None)
             else:                                                       # general per-point path
-                t = self.fc_t1(t_emb); t = t * torch.sigmoid(t)
+                if c["t_emb"].shape[0] != c["feat"].shape[0]:
+                    raise ValueError("t_emb must have one row per point (or one per scene)")
+                t = self.fc_t1(c["t_emb"]); t = t * torch.sigmoid(t)      # c["t_emb"] is already in internal numbering
                 t = self.fc_t2(t); c["t_emb"] = t * torch.sigmoid(t)
         c = self._c_embedding(c)
         c = self._run_stage(self._c_enc[0], c, cl, 0, exact); n = self._run_stage(self._n_enc[0], n, nl, 0, exact)
@@ -505,8 +509,13 @@ class PointTransformerV3(nn.Module):
 
     @staticmethod
     def _export(p):
-        """attach the reference-shaped serialization views callers may read"""
+        """back to the caller's numbering + the reference-shaped serialization views callers may read"""
         L = p["_level"]
+        ip = L.inv_perm.long()
+        p["feat"] = p["feat"][ip].contiguous()
+        p["coord"] = p["coord"][ip].contiguous()
+        p["batch"] = L.batch.long()                  # batch ids are sorted in both numberings
+        p.pop("conv_in", None)
         p["serialized_depth"] = L.depth
         p["serialized_code"] = L.serialized("code")
         p["serialized_order"] = L.serialized("order")

@@ -42,6 +42,9 @@ class Level:
         self.c0 = None           # physical row of the parent that defined the clusters
         self.pooling_depth = None
         self.m_dev = None
+        self.perm = None         # level 0 only: internal id r <-> original point perm[r] (see Plan)
+        self.inv_perm = None
+        self.orig = None         # level 0 only: (code, order, inverse) in the caller's numbering
         self._nbr = {}
         self._pm = {}
         self._pad_K = None       # patch size the reference would have cached its pad maps with
@@ -72,8 +75,17 @@ class Level:
 
     # ---- reference-shaped views (int64, logical row order) for API parity / tests ------
     def serialized(self, what):
-        t = {"code": self.code, "order": self.order, "inverse": self.inverse}[what]
+        """reference-shaped [k, n] int64 view in the CALLER's point numbering and logical row order"""
+        if self.orig is not None:
+            t = self.orig[{"code": 0, "order": 1, "inverse": 2}[what]]
+        else:
+            t = {"code": self.code, "order": self.order, "inverse": self.inverse}[what]
         return torch.stack([t[r][: self.n] for r in self.rowmap]).long()
+
+    def pooling_inverse(self):
+        """parent point -> pooled point (reference `cluster` / "pooling_inverse"), caller's numbering"""
+        c = self.cluster[: self.parent.n]
+        return c[self.parent.inv_perm.long()] if self.parent.inv_perm is not None else c
 
     def reference_pad_maps(self, K):
         """(pad, unpad, cu_seqlens) exactly as ptv3.py:188-244 would build them (host side, tiny)."""
@@ -129,12 +141,22 @@ class Plan:
         batch = ops.offset2batch(offset, N)
         code = ops.encode_codes(grid, batch, depth, orders)
         order, inverse = ops.argsort_rows(code, nbits)
+        # Internal numbering = rank along the first curve: point r of the working set is the caller's
+        # point perm[r].  Every level-0 kernel (conv tiles, patch gathers, LayerNorm rows) then walks
+        # memory in space-filling-curve order; inputs are gathered once and the logits scattered back.
+        perm, inv_perm = order[0], inverse[0]
+        pl = perm.long()
+        i_grid, i_batch = grid[pl].contiguous(), batch[pl].contiguous()
+        i_code = code[:, pl].contiguous()
+        i_order = inv_perm[order.long()].contiguous()          # original ids -> internal ids
+        i_inverse = inverse[:, pl].contiguous()
 
         def level0():
             L = Level()
-            L.n = L.cap = N; L.B = B; L.grid = grid; L.batch = batch
+            L.n = L.cap = N; L.B = B; L.grid = i_grid; L.batch = i_batch
             L.offset_host = offset_host; L.offset_dev = offset
-            L.code, L.order, L.inverse, L.depth = code, order, inverse, depth
+            L.code, L.order, L.inverse, L.depth = i_code, i_order, i_inverse, depth
+            L.perm, L.inv_perm, L.orig = perm, inv_perm, (code, order, inverse)
             return L
 
         # RNG order of the reference forward (ptv3.py:1761-1794): c.serialization, n.serialization,

@@ -98,12 +98,15 @@ def test_plan_vs_oracle(ops, counts):
         L = (plan.c_levels if net == "c" else plan.n_levels)[li]
         check(L, cc, oo, ii, pl["depth"])
         par_n = c.shape[1]
-        assert np.array_equal(L.cluster[:par_n].cpu().numpy(), pl["cluster"])            # pooling_inverse
+        assert np.array_equal(L.pooling_inverse().cpu().numpy(), pl["cluster"])           # pooling_inverse
         assert np.array_equal(L.idx_ptr[: L.n + 1].cpu().numpy(), pl["idx_ptr"])
-        head = L.head[: L.n].cpu().numpy()
-        assert np.array_equal(pl["cluster"][head], np.arange(L.n))                       # any member is a valid head
-        members = L.members().cpu().numpy()
+        head = L.head[: L.n].cpu().numpy()                                                # any member is a valid head
+        members = L.members().cpu().numpy()                                               # internal numbering
+        if L.parent.perm is not None:
+            members = L.parent.perm.cpu().numpy()[members]
+            head = L.parent.perm.cpu().numpy()[head]
         assert np.array_equal(pl["cluster"][members], np.repeat(np.arange(L.n), pl["counts"]))
+        assert np.array_equal(pl["cluster"][head], np.arange(L.n))
         g2 = g[pl["head_indices"]] >> pl["pooling_depth"]
         b2 = b[pl["head_indices"]]
         assert np.array_equal(L.grid[: L.n].cpu().numpy(), g2) and np.array_equal(L.batch[: L.n].cpu().numpy(), b2)
@@ -256,7 +259,8 @@ def test_attention_tcgen05_vs_flash_oracle(ops, counts, K, H):
 @pytest.mark.parametrize("counts,K,H", [((1000, 77, 129), 128, 4), ((2500,), 1024, 2), ((5000,), 1024, 4)])
 def test_attention_tcgen05_vs_real_flash_attn(ops, counts, K, H):
     """against the upstream kernel itself (flash_attn is installed on the GPU box): same inputs, same
-    varlen partition; both are fp16-in / fp32-accumulate / fp16-out, so 1e-3 abs"""
+    varlen partition; both are fp16-in / fp32-accumulate / fp16-out, so they may differ by one fp16 ulp of
+    the output (2^-10 relative: 1.95e-3 at |o| in [2,4)) on a few elements and agree elsewhere"""
     fa = pytest.importorskip("flash_attn")
     n, C = sum(counts), H * 16
     gen = torch.Generator().manual_seed(1)
@@ -270,4 +274,6 @@ def test_attention_tcgen05_vs_real_flash_attn(ops, counts, K, H):
     pm = ops.patch_maps(cu(order.astype(np.int32)), np.array(counts), K)
     q, k, v = ops.attn_pack(qkv.to(DEV), 0, C, 3, pm, H, False)
     out = ops.attn(q, k, v, pm, H, 0.25, n, False)
-    assert (out - ref).abs().max().item() < 1e-3
+    d = (out - ref).abs()
+    assert (d <= 2.0 ** -10 * ref.abs().clamp(min=0.5)).all().item()      # <= 1 fp16 ulp
+    assert d.mean().item() < 5e-5
