@@ -1,0 +1,388 @@
+// fp32-faithful GEMM on the 5th-gen tensor cores (tcgen05, kind::tf32, "3xTF32" split) with
+// (a) optionally GATHERED A rows -- the submanifold convolution as an implicit GEMM over taps --
+// and (b) a fused epilogue (bias, GELU, residual).  One kernel serves
+//   * spconv.SubMConv3d k=3 (ptv3.py:356-362, 1106-1123):  out[m] = b + sum_t in[nbr[m,t]] . W_t
+//   * every nn.Linear on the path (cpe.1, attn.qkv/proj, mlp.fc1/fc2, pooling/unpooling proj,
+//     cross-attention q/kv/proj: ptv3.py:185-186, 311-313, 359, 458, 575-581, 911-913)
+// (ptv3.py = pointcept/models/point_transformer_v3/point_transformer_v3m1_base.py)
+//
+// Numerics: every fp32 operand x is split into hi = x & 0xFFFFE000 (exact TF32) and lo = x - hi;
+// acc += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo with fp32 accumulation in TMEM: relative error ~2^-21,
+// i.e. fp32-class results (the reference runs these layers in fp32 at inference), at tensor-core
+// rate instead of the CUDA-core SGEMM / SIMT gather-GEMM this kernel replaces.
+//
+// CTA = 128 output rows x one N tile (<= 128 columns), 192 threads:
+//   warps 0-3  A producers (thread == row): gather 64 B of the row per k-chunk, split hi/lo, store to
+//              shared memory in the UMMA K-major core-matrix layout; afterwards the epilogue
+//              (TMEM lane == row): + bias, GELU, + residual, fp32 rows to HBM
+//   warp 4     B loader: one TMA bulk copy per k-chunk of the pre-split, pre-tiled weight block
+//   warp 5     MMA issuer: 6 x tcgen05.mma (M128 x N x K8) per k-chunk, commit -> frees the stage
+// 3-stage mbarrier ring; taps that no row of the tile has are skipped via a per-tile tap mask;
+// optional split over taps (grid.z) for levels with few rows (partials reduced by a second kernel).
+#include "common.cuh"
+
+namespace gt {
+
+constexpr int BM = 128;
+constexpr int NT = 128;                // max N tile (TMEM columns)
+constexpr int KC = 16;                 // fp32 elements per k-chunk (64 B per row)
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 192;
+constexpr int A_BYTES = BM * KC * 4;   // one of hi / lo
+constexpr int B_BYTES = NT * KC * 4;   // one of hi / lo (full tile; narrower tiles use a prefix)
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!done && clock64() - t0 > WAIT_TIMEOUT_CYCLES) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Params {
+  const float* A; long long lda;
+  const int32_t* idx; int T;              // idx [M, T] (row of A feeding tap t) or null => identity, T = 1
+  const uint32_t* tile_mask;              // per 128-row tile: bit t set <=> some row has tap t ; null => all taps
+  const float* Bp;                        // packed weights [T][K/KC][ntiles][2][NT*KC]
+  int M, N, K;
+  const float* bias; const float* res; long long ldr; int act;
+  float* out; long long ldo;
+  float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
+};
+
+struct Bars {
+  uint64_t full_a[STAGES], full_b[STAGES], empty[STAGES], acc;
+  uint32_t tmem_slot, pad;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Bars* bars = reinterpret_cast<Bars*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y, z = blockIdx.z;
+  const int ntiles = (p.N + NT - 1) / NT;
+  const int n0 = tile_n * NT;
+  const int wn = min(NT, p.N - n0);                 // valid output columns of this tile
+  const int un = (wn + 15) & ~15;                   // UMMA N (multiple of 16)
+  const int kch = p.K / KC;
+  // taps handled by this split
+  const int t_begin = (int)((long long)p.T * z / p.nsplit), t_end = (int)((long long)p.T * (z + 1) / p.nsplit);
+  const uint32_t mask = p.tile_mask ? p.tile_mask[tile_m] : 0xffffffffu;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bars->full_a[s]), 128);
+      mbar_init(smem_u32(&bars->full_b[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars->acc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)),
+                 "r"((uint32_t)NT)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+
+  // number of (tap, k-chunk) iterations of this CTA -- identical in every role
+  int n_iter = 0;
+  for (int t = t_begin; t < t_end; ++t)
+    if ((mask >> (t & 31)) & 1u || p.T > 32) n_iter += kch;
+
+  if (warp < 4) {
+    // ------------------------------- A producers -------------------------------
+    const int r = threadIdx.x;
+    const long long m = (long long)tile_m * BM + r;
+    const bool row_ok = m < p.M;
+    const uint32_t a_off = (uint32_t)((r >> 3) * (KC / 4) * 128 + (r & 7) * 16);
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      if (!((mask >> (t & 31)) & 1u) && p.T <= 32) continue;
+      long long src = -1;
+      if (row_ok) src = p.idx ? (long long)p.idx[m * p.T + t] : m;
+      const float4* row = src >= 0 ? reinterpret_cast<const float4*>(p.A + src * p.lda) : nullptr;
+      for (int kc = 0; kc < kch; ++kc, ++it) {
+        const int s = it % STAGES, u = it / STAGES;
+        float4 v[KC / 4];
+#pragma unroll
+        for (int j = 0; j < KC / 4; ++j) v[j] = row ? __ldg(row + kc * (KC / 4) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
+        uint8_t* hi = smem + s * STAGE_BYTES + a_off;
+        uint8_t* lo = hi + A_BYTES;
+#pragma unroll
+        for (int j = 0; j < KC / 4; ++j) {
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u); l.x = v[j].x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u); l.y = v[j].y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u); l.z = v[j].z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u); l.w = v[j].w - h.w;
+          *reinterpret_cast<float4*>(hi + j * 128) = h;
+          *reinterpret_cast<float4*>(lo + j * 128) = l;
+        }
+        fence_async_smem();
+        mbar_arrive(smem_u32(&bars->full_a[s]));
+      }
+    }
+    // --------------------------------- epilogue ---------------------------------
+    if (n_iter > 0) {
+      mbar_wait(smem_u32(&bars->acc), 0);
+      tc_fence_after();
+    }
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float* orow = nullptr;
+    if (row_ok) orow = (p.nsplit > 1) ? p.part + ((long long)z * p.M + m) * p.N + n0 : p.out + m * p.ldo + n0;
+    const float* rrow = (row_ok && p.res && p.nsplit == 1) ? p.res + m * p.ldr + n0 : nullptr;
+    for (int c0 = 0; c0 < un; c0 += 16) {
+      uint32_t acc[16];
+      if (n_iter > 0) {
+        tmem_ld16(tmem + lane_base + c0, acc);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0u;
+      }
+      if (!row_ok) continue;
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const int c = c0 + j4 * 4;
+        if (c >= wn) break;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x = __uint_as_float(acc[j4 * 4 + j]);
+          if (p.nsplit == 1) {
+            if (p.bias && c + j < wn) x += p.bias[n0 + c + j];
+            if (p.act == 1) x = gelu_erf(x);
+          }
+          o[j] = x;
+        }
+        if (c + 3 < wn) {
+          if (rrow) { const float4 q = *reinterpret_cast<const float4*>(rrow + c); o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w; }
+          *reinterpret_cast<float4*>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          for (int j = 0; j < 4 && c + j < wn; ++j) orow[c + j] = o[j] + (rrow ? rrow[c + j] : 0.f);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // -------------------------------- B loader --------------------------------
+    if (lane == 0) {
+      const uint32_t bbytes = (uint32_t)un * KC * 4;            // prefix of the hi / lo block (n-groups are outermost)
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        if (!((mask >> (t & 31)) & 1u) && p.T <= 32) continue;
+        for (int kc = 0; kc < kch; ++kc, ++it) {
+          const int s = it % STAGES, u = it / STAGES;
+          if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
+          const float* blk = p.Bp + ((((long long)t * kch + kc) * ntiles + tile_n) * 2) * (NT * KC);
+          uint8_t* b_hi = smem + s * STAGE_BYTES + 2 * A_BYTES;
+          mbar_expect_tx(smem_u32(&bars->full_b[s]), 2 * bbytes);
+          tma_load_1d(smem_u32(b_hi), blk, bbytes, smem_u32(&bars->full_b[s]));
+          tma_load_1d(smem_u32(b_hi + B_BYTES), blk + NT * KC, bbytes, smem_u32(&bars->full_b[s]));
+        }
+      }
+    }
+  } else {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0 && n_iter > 0) {
+      // kind::tf32: D fp32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(un >> 3) << 17) | ((128u >> 4) << 24);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % STAGES, u = it / STAGES;
+        mbar_wait(smem_u32(&bars->full_a[s]), (uint32_t)(u & 1));
+        mbar_wait(smem_u32(&bars->full_b[s]), (uint32_t)(u & 1));
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < KC / 8; ++ks) {                    // K = 8 per MMA = 2 core matrices = 256 B
+          const uint64_t ah = make_desc(a_hi + ks * 256, 128, (KC / 4) * 128), al = make_desc(a_lo + ks * 256, 128, (KC / 4) * 128);
+          const uint64_t bh = make_desc(b_hi + ks * 256, 128, (KC / 4) * 128), bl = make_desc(b_lo + ks * 256, 128, (KC / 4) * 128);
+          umma_tf32(tmem, al, bh, idesc, (it | ks) != 0);        // small terms first
+          umma_tf32(tmem, ah, bl, idesc, 1);
+          umma_tf32(tmem, ah, bh, idesc, 1);
+        }
+        umma_commit(smem_u32(&bars->empty[s]));
+      }
+      umma_commit(smem_u32(&bars->acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)NT) : "memory");
+  }
+}
+
+// out[m][n] = act(bias[n] + sum_z part[z][m][n]) + res[m][n]
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int nsplit, long long M, int N,
+                                     const float* __restrict__ bias, const float* __restrict__ res, long long ldr,
+                                     int act, float* __restrict__ out, long long ldo) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const long long m = i / N;
+  const int n = (int)(i % N);
+  float s = 0.f;
+  for (int z = 0; z < nsplit; ++z) s += part[(long long)z * M * N + i];
+  if (bias) s += bias[n];
+  if (act == 1) s = gelu_erf(s);
+  if (res) s += res[m * ldr + n];
+  out[m * ldo + n] = s;
+}
+
+// per 128-row tile: OR over rows of (nbr[row][t] >= 0) << t     (T <= 32)
+__global__ void tile_mask_kernel(const int32_t* __restrict__ nbr, long long M, int T, uint32_t* __restrict__ mask) {
+  const int tile = blockIdx.x;
+  const long long m = (long long)tile * BM + threadIdx.x;
+  uint32_t b = 0;
+  if (m < M)
+    for (int t = 0; t < T; ++t) b |= (nbr[m * T + t] >= 0 ? 1u : 0u) << t;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b |= __shfl_xor_sync(0xffffffffu, b, o);
+  __shared__ uint32_t w[BM / 32];
+  if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) mask[tile] = w[0] | w[1] | w[2] | w[3];
+}
+
+// pack W [T][K][N] (fp32, row-major: the tap-major transposed conv weight, or weight^T of a Linear) into
+// Bp [T][K/KC][ntiles][2][NT*KC]: K-major core-matrix tiles, hi then lo.
+__global__ void pack_b_kernel(const float* __restrict__ W, int T, int K, int N, float* __restrict__ Bp) {
+  const int ntiles = (N + NT - 1) / NT, kch = K / KC;
+  const long long total = (long long)T * kch * ntiles * NT * KC;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // destination element order inside a block: (n/8, k/4, n%8, k%4)
+  const int e = (int)(i % (NT * KC));
+  const long long blk = i / (NT * KC);
+  const int tn = (int)(blk % ntiles);
+  const int kc = (int)((blk / ntiles) % kch);
+  const int t = (int)(blk / ((long long)ntiles * kch));
+  const int k4 = e % 4, n8 = (e / 4) % 8, kg = (e / 32) % (KC / 4), ng = e / (32 * (KC / 4));
+  const int n = tn * NT + ng * 8 + n8, k = kc * KC + kg * 4 + k4;
+  const float x = n < N ? W[((long long)t * K + k) * N + n] : 0.f;
+  const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  float* dst = Bp + blk * 2 * (NT * KC);
+  dst[e] = h;
+  dst[NT * KC + e] = x - h;
+}
+
+}  // namespace gt
+
+CDSEG_API size_t cdseg_gemm_packed_b_floats(int T, int K, int N) {
+  return (size_t)T * (K / gt::KC) * ((N + gt::NT - 1) / gt::NT) * 2 * gt::NT * gt::KC;
+}
+
+// W: fp32 [T][K][N] -> Bp (cdseg_gemm_packed_b_floats floats).  K % 16 == 0.
+CDSEG_API int cdseg_gemm_pack_b(const float* W, int T, int K, int N, float* Bp, void* stream) {
+  if (T <= 0 || K <= 0 || (K % gt::KC) || N <= 0) return CDSEG_EINVAL;
+  const long long total = (long long)T * (K / gt::KC) * ((N + gt::NT - 1) / gt::NT) * gt::NT * gt::KC;
+  gt::pack_b_kernel<<<cdseg_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(W, T, K, N, Bp);
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
+
+// mask: uint32 [ceil(M/128)]
+CDSEG_API int cdseg_tile_tap_mask(const int32_t* nbr, int64_t M, int T, uint32_t* mask, void* stream) {
+  if (T <= 0 || T > 32) return CDSEG_EINVAL;
+  if (M == 0) return CDSEG_OK;
+  gt::tile_mask_kernel<<<cdseg_div_up(M, gt::BM), gt::BM, 0, (cudaStream_t)stream>>>(nbr, M, T, mask);
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
+
+CDSEG_API size_t cdseg_gemm_tc_workspace_bytes(int64_t M, int N, int nsplit) {
+  return nsplit > 1 ? (size_t)nsplit * M * N * sizeof(float) : 0;
+}
+
+// out[M,N] = act(bias + sum_t A[idx[:,t]] @ W_t) + res   (see include/cdseg_b200.h)
+CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int T, const uint32_t* tile_mask,
+                            const float* Bp, int64_t M, int N, int K, const float* bias, const float* res, int64_t ldr,
+                            int act, float* out, int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M < 0 || N <= 0 || K <= 0 || (K % gt::KC) || (lda & 3) || (ldo & 3) || (res && (ldr & 3)) || T <= 0 ||
+      (idx == nullptr && T != 1) || nsplit < 1 || nsplit > T || (tile_mask && T > 32))
+    return CDSEG_EINVAL;
+  if (M == 0) return CDSEG_OK;
+  if (workspace_bytes < cdseg_gemm_tc_workspace_bytes(M, N, nsplit)) return CDSEG_ENOSPC;
+  const size_t smem = (size_t)gt::STAGES * gt::STAGE_BYTES + sizeof(gt::Bars) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gt::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  gt::Params p;
+  p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp;
+  p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.ldr = ldr; p.act = act; p.out = out; p.ldo = ldo;
+  p.part = (float*)workspace; p.nsplit = nsplit;
+  dim3 g(cdseg_div_up(M, gt::BM), (N + gt::NT - 1) / gt::NT, nsplit);
+  gt::gemm_tc_kernel<<<g, gt::NTHREADS, smem, st>>>(p);
+  CDSEG_COUNT_LAUNCH(1);
+  if (nsplit > 1) {
+    gt::splitk_reduce_kernel<<<cdseg_div_up(M * N, 256), 256, 0, st>>>((const float*)workspace, nsplit, M, N, bias, res,
+                                                                       ldr, act, out, ldo);
+    CDSEG_COUNT_LAUNCH(1);
+  }
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
