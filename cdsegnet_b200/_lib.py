@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
-SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu"]
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "gemm_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
@@ -94,6 +94,11 @@ SIGNATURES = {
     "cdseg_scale_shift_act": (_I, [_P, _P, _P, _I, _L, _I, _P, _P]),
     "cdseg_small_linear": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "cdseg_rows_uniform": (_I, [_P, _P, _P, _L, _I, _P, _P]),
+    "cdseg_gemm_packed_b_floats": (_Z, [_I, _I, _I]),
+    "cdseg_gemm_pack_b": (_I, [_P, _I, _I, _I, _P, _P]),
+    "cdseg_tile_tap_mask": (_I, [_P, _L, _I, _P, _P]),
+    "cdseg_gemm_tc_workspace_bytes": (_Z, [_L, _I, _I]),
+    "cdseg_gemm_tc": (_I, [_P, _L, _P, _I, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P, _L, _I, _P, _Z, _P]),
 }
 
 _lib = None

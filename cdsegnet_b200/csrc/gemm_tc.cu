@@ -91,7 +91,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 struct Params {
   const float* A; long long lda;
-  const int32_t* idx; int T;              // idx [M, T] (row of A feeding tap t) or null => identity, T = 1
+  const int32_t* idx; int T;              // idx [M, T] (row of A feeding tap t); null => row m, tap t = columns [tK, (t+1)K)
   const uint32_t* tile_mask;              // per 128-row tile: bit t set <=> some row has tap t ; null => all taps
   const float* Bp;                        // packed weights [T][K/KC][ntiles][2][NT*KC]
   int M, N, K;
@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const Params p) {
       if (!((mask >> (t & 31)) & 1u) && p.T <= 32) continue;
       long long src = -1;
       if (row_ok) src = p.idx ? (long long)p.idx[m * p.T + t] : m;
-      const float4* row = src >= 0 ? reinterpret_cast<const float4*>(p.A + src * p.lda) : nullptr;
+      // without idx, "tap" t is the t-th K-slice of the same row (split-K of a plain Linear)
+      const float4* row = src >= 0 ? reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) : nullptr;
       for (int kc = 0; kc < kch; ++kc, ++it) {
         const int s = it % STAGES, u = it / STAGES;
         float4 v[KC / 4];
@@ -360,7 +361,7 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
                             void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (M < 0 || N <= 0 || K <= 0 || (K % gt::KC) || (lda & 3) || (ldo & 3) || (res && (ldr & 3)) || T <= 0 ||
-      (idx == nullptr && T != 1) || nsplit < 1 || nsplit > T || (tile_mask && T > 32))
+      nsplit < 1 || nsplit > T || (tile_mask && T > 32))
     return CDSEG_EINVAL;
   if (M == 0) return CDSEG_OK;
   if (workspace_bytes < cdseg_gemm_tc_workspace_bytes(M, N, nsplit)) return CDSEG_ENOSPC;

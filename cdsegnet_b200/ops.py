@@ -233,3 +233,51 @@ def launch_count():
 
 def launch_count_reset():
     _lib.load().cdseg_launch_count_reset()
+
+
+# ---------------------------------------------------------------- tensor-core GEMM (3xTF32)
+def gemm_pack_b(W):
+    """W fp32 [T, K, N] -> packed operand blocks for gemm_tc (cache the result per weight)."""
+    lib = _lib.load()
+    T, K, N = W.shape
+    Bp = torch.empty(lib.cdseg_gemm_packed_b_floats(T, K, N), dtype=torch.float32, device=W.device)
+    check(lib.cdseg_gemm_pack_b(_p(W, torch.float32), T, K, N, _p(Bp), _stream()), "gemm_pack_b")
+    return Bp
+
+
+def tile_tap_mask(nbr):
+    M, T = nbr.shape
+    mask = torch.empty((M + 127) // 128, dtype=torch.int32, device=nbr.device)
+    check(_lib.load().cdseg_tile_tap_mask(_p(nbr, torch.int32), M, T, _p(mask), _stream()), "tile_tap_mask")
+    return mask
+
+
+GEMM_MODE = "tc"      # "tc": tcgen05 3xTF32 kernels for conv + linears ; "simt": round-1a SIMT conv + cuBLAS SGEMM
+
+
+def pick_split(tiles, T):
+    """taps/K-slices are split over grid.z until ~200 CTAs exist (levels with few rows would otherwise
+    leave most of the 148 SMs idle while one CTA streams the whole weight)"""
+    if tiles >= 120 or T == 1:
+        return 1
+    want = -(-200 // tiles)
+    for s in range(1, T + 1):
+        if T % s == 0 and s >= want:
+            return s
+    return T
+
+
+def gemm_tc(A, Bp, N, K, idx=None, tile_mask=None, bias=None, res=None, act=0, nsplit=1, M=None, T=None):
+    """out[M,N] = act(bias + sum_t A[idx[:,t]] @ W_t) + res, fp32 in/out, tcgen05 3xTF32 inside.
+    Without idx, T > 1 means: A row m is cut into T K-slices of width K (split-K of a Linear)."""
+    lib = _lib.load()
+    if T is None:
+        T = idx.shape[1] if idx is not None else 1
+    M = (idx.shape[0] if idx is not None else A.shape[0]) if M is None else M
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    nb = lib.cdseg_gemm_tc_workspace_bytes(M, N, nsplit)
+    ws = _ws(nb, A.device) if nb else None
+    check(lib.cdseg_gemm_tc(_p(A, torch.float32), A.shape[1], _p(idx), T, _p(tile_mask), _p(Bp, torch.float32), M, N, K,
+                            _p(bias), _p(res), res.shape[1] if res is not None else 0, act, _p(out), N, nsplit, _p(ws), nb,
+                            _stream()), "gemm_tc")
+    return out

@@ -86,7 +86,67 @@ class SubMConv3d(nn.Module):
 
     def forward(self, x, level, ep_scale=None, ep_shift=None, ep_gelu=False):
         b = self.bias.detach() if self.bias is not None else None
+        if ops.GEMM_MODE == "tc" and self.k == 3 and self.cin % 16 == 0 and ep_scale is None:
+            # implicit GEMM over the 27 taps on the tensor cores (3xTF32), absent taps skipped per 128-row tile
+            Bp = _PACK.get((id(self.weight), "conv"), [self.weight], lambda: ops.gemm_pack_b(self.wt()))
+            nbr = level.nbr(3)
+            tiles = -(-x.shape[0] // 128) * -(-self.cout // 128)
+            return ops.gemm_tc(x, Bp, self.cout, self.cin, idx=nbr, tile_mask=level.tile_mask(3), bias=b,
+                               nsplit=ops.pick_split(tiles, 27))
         return ops.subm_conv(x, level.nbr(self.k), self.wt(), b, self.k, ep_scale, ep_shift, ep_gelu)
+
+
+class _PackCache:
+    """packed tensor-core operand blocks, rebuilt when a source parameter / buffer changes"""
+
+    def __init__(self):
+        self.c = {}
+
+    def get(self, key, tensors, build):
+        sig = tuple((t._version, t.data_ptr()) for t in tensors if t is not None)
+        e = self.c.get(key)
+        if e is None or e[0] != sig:
+            e = (sig, build())
+            self.c[key] = e
+        return e[1]
+
+
+_PACK = _PackCache()
+
+
+def linear(x, w, b=None, act=0, res=None, bn=None, cols=None):
+    """act(bn(x @ w[:, cols]^T + b)) + res.  tcgen05 3xTF32 GEMM with everything fused in the epilogue
+    (eval-mode BatchNorm is folded into the packed weight/bias); cuBLAS SGEMM path for ops.GEMM_MODE == "simt"."""
+    K = x.shape[1]
+    N = w.shape[0]
+    if ops.GEMM_MODE == "tc" and K % 16 == 0:
+        def build():
+            wf = w.detach().float()
+            if cols is not None:
+                wf = wf[:, cols[0]:cols[1]]
+            bf = b.detach().float() if b is not None else None
+            if bn is not None:
+                sc, sh = bn_fold(bn)
+                wf = wf * sc[:, None]
+                bf = (bf * sc + sh) if bf is not None else sh
+            return ops.gemm_pack_b(wf.t().contiguous()[None]), (bf.contiguous() if bf is not None else None)
+        srcs = [w, b] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
+        Bp, bias = _PACK.get((id(w), cols), srcs, build)
+        M = x.shape[0]
+        tiles = -(-M // 128) * -(-N // 128)
+        T = 1
+        if tiles < 120 and K >= 256:                       # few rows, long K: split K over grid.z
+            T = K // 64
+        ns = ops.pick_split(tiles, T)
+        return ops.gemm_tc(x, Bp, N, K // T, bias=bias, res=res, act=act, nsplit=ns, T=T)
+    wf = w if cols is None else w[:, cols[0]:cols[1]]
+    y = F.linear(x, wf, b)
+    if bn is not None:
+        sc, sh = bn_fold(bn)
+        y = ops.scale_shift_act(y, sc, sh, act)
+    elif act == 1:
+        y = F.gelu(y)
+    return y if res is None else y + res
 
 
 def bn_fold(bn):
@@ -107,8 +167,9 @@ class MLP(nn.Module):
         self.act = nn.GELU()
         self.fc2 = nn.Linear(hidden, c)
 
-    def forward(self, x):
-        return self.fc2(F.gelu(self.fc1(x)))
+    def forward(self, x, res=None):
+        h = linear(x, self.fc1.weight, self.fc1.bias, act=1)                 # fc1 + GELU fused
+        return linear(h, self.fc2.weight, self.fc2.bias, res=res)            # fc2 + residual fused
 
 
 class SerializedAttention(nn.Module):
@@ -128,10 +189,10 @@ class SerializedAttention(nn.Module):
 
     def forward(self, x, level, exact):
         pm = level.patch_maps(self.order_index, self.patch_size)
-        qkv = self.qkv(x)
+        qkv = linear(x, self.qkv.weight, self.qkv.bias)
         q, k, v = ops.attn_pack(qkv, 0, self.channels, 3, pm, self.num_heads, exact)
         o = ops.attn(q, k, v, pm, self.num_heads, self.scale, x.shape[0], exact)
-        return self.proj(o)
+        return linear(o, self.proj.weight, self.proj.bias)
 
 
 class Block(nn.Module):
@@ -154,20 +215,20 @@ class Block(nn.Module):
         x = point["feat"]
         conv_in = point.pop("conv_in", x)             # stale sparse_conv_feat quirk, see SerializedUnpooling
         y = self.cpe[0](conv_in, level)
-        y = self.cpe[1](y)
+        y = linear(y, self.cpe[1].weight, self.cpe[1].bias)
         _, y = ops.add_layernorm(y, gamma=self.cpe[2].weight, beta=self.cpe[2].bias, eps=self.cpe[2].eps, want_sum=False)
         t = tb = None
         if self.T_dim != -1 and "t_scene" in point:    # per-scene timestep rows, broadcast by batch id
             t = ops.small_linear(point["t_scene"], self.t_mlp.weight, self.t_mlp.bias)
             tb = level.batch[: level.n]
         elif self.T_dim != -1 and "t_emb" in point:    # general (per-point) path
-            y = y + self.t_mlp(point["t_emb"])
+            y = linear(point["t_emb"], self.t_mlp.weight, self.t_mlp.bias, res=y)
         n1 = self.norm1[0]
         x1, h = ops.add_layernorm(x, y, t, tb, n1.weight, n1.bias, n1.eps)
         a = self.attn(h, level, exact)
         n2 = self.norm2[0]
         x2, h = ops.add_layernorm(x1, a, gamma=n2.weight, beta=n2.bias, eps=n2.eps)
-        point["feat"] = x2 + self.mlp[0](h)
+        point["feat"] = self.mlp[0](h, res=x2)
         return point
 
 
@@ -184,7 +245,7 @@ class SerializedPooling(nn.Module):
     def forward(self, point, child_level):
         par = point["_level"]
         scale, shift = bn_fold(self.norm[0])
-        p = self.proj(point["feat"])
+        p = linear(point["feat"], self.proj.weight, self.proj.bias)
         feat, coord = ops.pool_reduce(p, point["coord"], child_level.members(), child_level.idx_ptr, child_level.n,
                                       scale, shift, True)
         new = Point(feat=feat, coord=coord, _level=child_level, pooling_parent=point,
@@ -220,10 +281,8 @@ class SerializedUnpooling(nn.Module):
     def forward(self, point):
         parent = point.pop("pooling_parent")
         cluster = point.pop("pooling_inverse")
-        s1, h1 = bn_fold(self.proj[1])
-        s2, h2 = bn_fold(self.proj_skip[1])
-        up = ops.scale_shift_act(self.proj[0](point["feat"]), s1, h1, 1)
-        skip = ops.scale_shift_act(self.proj_skip[0](parent["feat"]), s2, h2, 1)
+        up = linear(point["feat"], self.proj[0].weight, self.proj[0].bias, act=1, bn=self.proj[1])
+        skip = linear(parent["feat"], self.proj_skip[0].weight, self.proj_skip[0].bias, act=1, bn=self.proj_skip[1])
         # reference quirk: parent.feat is assigned directly below (ptv3.py:608-625), so
         # parent.sparse_conv_feat -- what the next block's CPE conv reads -- keeps `skip`.
         parent["conv_in"] = skip
@@ -231,8 +290,8 @@ class SerializedUnpooling(nn.Module):
             parent["feat"] = ops.unpool_add(skip, up, cluster, self.alpha)
         else:
             w = self.proj_cat[0].weight
-            a = F.linear(skip, w[:, : self.cout])
-            bb = F.linear(up, w[:, self.cout:], self.proj_cat[0].bias)
+            a = linear(skip, w, None, cols=(0, self.cout))
+            bb = linear(up, w, self.proj_cat[0].bias, cols=(self.cout, 2 * self.cout))
             parent["feat"] = ops.unpool_add(a, bb, cluster, self.alpha)
         return parent
 
@@ -275,10 +334,10 @@ class SerializedCrossAttention(nn.Module):
             raise ValueError("TransferModule needs equally sized q / kv levels (ptv3.py:1008-1010)")
         kv_row = kv_level.order[kv_level.rowmap[self.order_index]][: kv_level.n]
         pm_kv = ops.patch_maps(kv_row, q_level.scene_count(), pm["K"])
-        (q,) = ops.attn_pack(self.q(xq), 0, self.C, 1, pm, self.H, exact)
-        k, v = ops.attn_pack(self.kv(xkv), 0, self.C, 2, pm_kv, self.H, exact)
+        (q,) = ops.attn_pack(linear(xq, self.q.weight, self.q.bias), 0, self.C, 1, pm, self.H, exact)
+        k, v = ops.attn_pack(linear(xkv, self.kv.weight, self.kv.bias), 0, self.C, 2, pm_kv, self.H, exact)
         o = ops.attn(q, k, v, pm, self.H, self.scale, xq.shape[0], exact)
-        return self.proj(o)
+        return linear(o, self.proj.weight, self.proj.bias)
 
 
 class CrossBlock(nn.Module):
@@ -302,7 +361,7 @@ class CrossBlock(nn.Module):
 
     @staticmethod
     def _cpe(seq, x, level):
-        y = seq[1](seq[0](x, level))
+        y = linear(seq[0](x, level), seq[1].weight, seq[1].bias)
         return ops.add_layernorm(y, gamma=seq[2].weight, beta=seq[2].bias, eps=seq[2].eps, want_sum=False)[1]
 
     def forward(self, q_point, kv_point, exact):
@@ -317,7 +376,7 @@ class CrossBlock(nn.Module):
         if self.tm_feat != 1.0:
             a = a * self.tm_feat
         q2, h = ops.add_layernorm(q1, a, gamma=n2.weight, beta=n2.bias, eps=n2.eps)
-        q_point["feat"] = q2 + self.mlp[0](h)
+        q_point["feat"] = self.mlp[0](h, res=q2)
         return q_point
 
 
@@ -469,7 +528,7 @@ class PointTransformerV3(nn.Module):
                 n = self._run_stage(self._n_enc[s], n, nl, s, exact)
             for j in range(len(nl) - 1):
                 n = self._run_stage(self._n_dec[j], n, nl, None, exact)
-            n["feat"] = self._n_head(n["feat"]).contiguous()
+            n["feat"] = linear(n["feat"], self._n_head.weight, self._n_head.bias)
             return self._export(n)
 
         cl = plan.c_levels
@@ -503,8 +562,8 @@ class PointTransformerV3(nn.Module):
         n = self._run_stage(self._n_dec[0], n, nl, None, exact); n = self._run_stage(self._n_dec[1], n, nl, None, exact)
         c = self._run_stage(self._c_dec[1], c, cl, None, exact)
         n = self._run_stage(self._n_dec[2], n, nl, None, exact); n = self._run_stage(self._n_dec[3], n, nl, None, exact)
-        c["feat"] = self._c_head(c["feat"]).contiguous()
-        n["feat"] = self._n_head(n["feat"]).contiguous()
+        c["feat"] = linear(c["feat"], self._c_head.weight, self._c_head.bias)
+        n["feat"] = linear(n["feat"], self._n_head.weight, self._n_head.bias)
         return self._export(c), self._export(n)
 
     @staticmethod

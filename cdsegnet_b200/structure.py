@@ -58,6 +58,13 @@ class Level:
             self._nbr[ksize] = ops.nbr_build(self.grid[: self.n], self.batch[: self.n], ksize)
         return self._nbr[ksize]
 
+    def tile_mask(self, ksize):
+        """per 128-row tile bitmask of the taps that occur (lets the conv GEMM skip absent taps)"""
+        key = ("mask", ksize)
+        if key not in self._nbr:
+            self._nbr[key] = ops.tile_tap_mask(self.nbr(ksize))
+        return self._nbr[key]
+
     def patch_maps(self, order_index, K):
         """slot maps of logical curve `order_index`.  Like the reference (ptv3.py:191-244 caches
         "pad"/"unpad" on the Point), the FIRST patch size used at a level sticks."""

@@ -112,6 +112,22 @@ int cdseg_small_linear(const float* x, const float* W, const float* bias, int ac
 int cdseg_rows_uniform(const float* x, const int32_t* batch, const int64_t* offset, int64_t n, int C, int32_t* flag,
                        void* stream);
 
+/* ---- fp32-faithful tensor-core GEMM (tcgen05 kind::tf32, 3xTF32 split) with gathered A rows and fused epilogue:
+ *      replaces spconv.SubMConv3d k=3 (ptv3.py:356-362, 1106-1123) as an implicit GEMM over taps AND every nn.Linear on
+ *      the path (ptv3.py:185-186, 311-313, 359, 458, 575-581, 911-913) ------------------------------------------ */
+/* W fp32 [T][K][N] (tap-major transposed conv weight, or weight^T of a Linear with T=1; K % 16 == 0)
+ * -> Bp: cdseg_gemm_packed_b_floats(T,K,N) floats of pre-split (hi|lo), pre-tiled UMMA operand blocks */
+size_t cdseg_gemm_packed_b_floats(int T, int K, int N);
+int cdseg_gemm_pack_b(const float* W, int T, int K, int N, float* Bp, void* stream);
+/* mask[tile] bit t = some row of the 128-row tile has neighbour t (nbr int32 [M,T], T <= 32) */
+int cdseg_tile_tap_mask(const int32_t* nbr, int64_t M, int T, uint32_t* mask, void* stream);
+/* out[M,N] = act(bias + sum_t A[idx[m,t]] @ W_t) + res ; idx NULL => row m, tap t = its t-th K-slice (split-K Linear); tile_mask NULL => all
+ * taps; act 0 none / 1 GELU(erf); nsplit > 1 splits the taps over grid.z (partials in workspace, reduced by a 2nd kernel) */
+size_t cdseg_gemm_tc_workspace_bytes(int64_t M, int N, int nsplit);
+int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int T, const uint32_t* tile_mask, const float* Bp,
+                  int64_t M, int N, int K, const float* bias, const float* res, int64_t ldr, int act, float* out,
+                  int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,15 @@ def test_general_t_emb_path_matches_fast_path():
     c, nn_ = m(dict(base, feat=t(z["noise"]).to(DEV), t_emb=te), dict(base, feat=t(z["feat"]).to(DEV)), perm_fn=replay(z["perms"]))
     assert np.abs(nn_["feat"].cpu().numpy() - z["n_feat"]).max() < 1e-3
     assert np.abs(c["feat"].cpu().numpy() - z["c_feat"]).max() < 1e-3
+
+
+def test_simt_gemm_mode_still_matches():
+    """the round-1a path (SIMT gather-GEMM conv + cuBLAS SGEMM linears) stays available and parity-green"""
+    from cdsegnet_b200 import ops
+    z, cfg, shapes = load_case("case2_batch2")
+    ops.GEMM_MODE = "simt"
+    try:
+        c, n, _ = run_cuda(z, cfg, shapes, exact=True)
+    finally:
+        ops.GEMM_MODE = "tc"
+    assert np.abs(n["feat"].cpu().numpy() - z["n_feat"]).max() < 1e-3

@@ -277,3 +277,49 @@ def test_attention_tcgen05_vs_real_flash_attn(ops, counts, K, H):
     d = (out - ref).abs()
     assert (d <= 2.0 ** -10 * ref.abs().clamp(min=0.5)).all().item()      # <= 1 fp16 ulp
     assert d.mean().item() < 5e-5
+
+
+# ------------------------------------------------------------------ tcgen05 3xTF32 GEMM
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("M,K,N,act,use_res,T", [(1000, 32, 96, 0, False, 1), (5000, 32, 128, 1, False, 1), (129, 16, 16, 0, True, 1),
+                                                  (300, 64, 20, 0, False, 1), (777, 96, 288, 1, True, 1), (816, 2048, 512, 0, True, 32),
+                                                  (816, 512, 1536, 0, False, 8), (3023, 256, 1024, 1, False, 1), (1, 64, 6, 0, False, 1)])
+def test_gemm_tc_linear_vs_fp64(ops, M, K, N, act, use_res, T):
+    """fp32-faithful: 3xTF32 split keeps the result within ~1e-5 relative of an fp64 reference (cuBLAS SGEMM class)"""
+    gen = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=gen); w = torch.randn(N, K, generator=gen) / K ** 0.5
+    b = torch.randn(N, generator=gen); r = torch.randn(M, N, generator=gen) if use_res else None
+    ref = x.double() @ w.double().t() + b.double()
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    if use_res:
+        ref = ref + r.double()
+    Bp = ops.gemm_pack_b(w.t().contiguous()[None].to(DEV))
+    tiles = -(-M // 128) * -(-N // 128)
+    ns = ops.pick_split(tiles, T) if T > 1 else 1
+    out = ops.gemm_tc(x.to(DEV), Bp, N, K // T, bias=b.to(DEV), res=r.to(DEV) if use_res else None, act=act, nsplit=ns, T=T)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("c,ns", [(16, 1), (32, 1), (64, 3), (96, 1), (128, 9), (256, 27)])
+def test_gemm_tc_conv_vs_oracle(ops, c, ns):
+    sc = _scene((1500, 600))
+    g, b = sc["grid_coord"], S.offset2batch(sc["offset"])
+    gen = torch.Generator().manual_seed(c)
+    x = torch.randn(len(g), c, generator=gen)
+    w = torch.randn(c, 3, 3, 3, c, generator=gen) / (27 * c * 0.4) ** 0.5
+    bias = torch.randn(c, generator=gen)
+    ref = O.subm_conv3d(x, torch.from_numpy(b), torch.from_numpy(g), w, bias)
+    nbr = ops.nbr_build(cu(g), cu(b, torch.int32), 3)
+    mask = ops.tile_tap_mask(nbr)
+    nb = nbr.cpu().numpy()
+    exp_mask = np.array([np.bitwise_or.reduce((nb[i:i + 128] >= 0).astype(np.int64) << np.arange(27), axis=None)
+                         for i in range(0, len(nb), 128)])
+    assert np.array_equal(mask.cpu().numpy().astype(np.int64) & 0x7ffffff, exp_mask)
+    Bp = ops.gemm_pack_b(w.reshape(c, 27, c).permute(1, 2, 0).contiguous().to(DEV))
+    out = ops.gemm_tc(x.to(DEV), Bp, c, c, idx=nbr, tile_mask=mask, bias=bias.to(DEV), nsplit=ns)
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max() < 3e-5
