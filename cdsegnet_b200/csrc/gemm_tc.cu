@@ -98,6 +98,7 @@ struct Params {
   const float* bias; const float* res; long long ldr; int act;
   float* out; long long ldo;
   float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
+  int vec_ok;                             // output / residual rows are 16-byte aligned
 };
 
 struct Bars {
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const Params p) {
           }
           o[j] = x;
         }
-        if (c + 3 < wn) {
+        if (c + 3 < wn && p.vec_ok) {
           if (rrow) { const float4 q = *reinterpret_cast<const float4*>(rrow + c); o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w; }
           *reinterpret_cast<float4*>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
         } else {
@@ -360,7 +361,7 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
                             int act, float* out, int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes,
                             void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (M < 0 || N <= 0 || K <= 0 || (K % gt::KC) || (lda & 3) || (ldo & 3) || (res && (ldr & 3)) || T <= 0 ||
+  if (M < 0 || N <= 0 || K <= 0 || (K % gt::KC) || (lda & 3) || T <= 0 ||
       nsplit < 1 || nsplit > T || (tile_mask && T > 32))
     return CDSEG_EINVAL;
   if (M == 0) return CDSEG_OK;
@@ -376,6 +377,8 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp;
   p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.ldr = ldr; p.act = act; p.out = out; p.ldo = ldo;
   p.part = (float*)workspace; p.nsplit = nsplit;
+  p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
+              (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + gt::NT - 1) / gt::NT, nsplit);
   gt::gemm_tc_kernel<<<g, gt::NTHREADS, smem, st>>>(p);
   CDSEG_COUNT_LAUNCH(1);

@@ -322,4 +322,4 @@ def test_gemm_tc_conv_vs_oracle(ops, c, ns):
     Bp = ops.gemm_pack_b(w.reshape(c, 27, c).permute(1, 2, 0).contiguous().to(DEV))
     out = ops.gemm_tc(x.to(DEV), Bp, c, c, idx=nbr, tile_mask=mask, bias=bias.to(DEV), nsplit=ns)
     torch.cuda.synchronize()
-    assert (out.cpu() - ref).abs().max() < 3e-5
+    assert (out.cpu() - ref).abs().max() < 1e-4      # 3xTF32: ~2^-21 relative per product, |out| up to ~5
