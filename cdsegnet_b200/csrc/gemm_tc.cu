@@ -17,7 +17,7 @@
 //              (TMEM lane == row): + bias, GELU, + residual, fp32 rows to HBM
 //   warp 4     B loader: one TMA bulk copy per k-chunk of the pre-split, pre-tiled weight block
 //   warp 5     MMA issuer: 6 x tcgen05.mma (M128 x N x K8) per k-chunk, commit -> frees the stage
-// 3-stage mbarrier ring; taps that no row of the tile has are skipped via a per-tile tap mask;
+// 2-stage mbarrier ring, 3 CTAs per SM; taps that no row of the tile has are skipped via a per-tile tap mask;
 // optional split over taps (grid.z) for levels with few rows (partials reduced by a second kernel).
 #include "common.cuh"
 
@@ -26,7 +26,7 @@ namespace gt {
 constexpr int BM = 128;
 constexpr int NT = 128;                // max N tile (TMEM columns)
 constexpr int KC = 16;                 // fp32 elements per k-chunk (64 B per row)
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
 constexpr int NTHREADS = 192;
 constexpr int A_BYTES = BM * KC * 4;   // one of hi / lo
 constexpr int B_BYTES = NT * KC * 4;   // one of hi / lo (full tile; narrower tiles use a prefix)
@@ -106,7 +106,7 @@ struct Bars {
   uint32_t tmem_slot, pad;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + STAGES * STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,45 +181,65 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const Params p) {
       }
     }
     // --------------------------------- epilogue ---------------------------------
+    // TMEM (lane == row) -> registers -> bias/GELU -> shared-memory staging (each warp only touches its own
+    // 32 rows, so __syncwarp suffices) -> coalesced 128-byte row segments to HBM (+ residual, read coalesced).
     if (n_iter > 0) {
-      mbar_wait(smem_u32(&bars->acc), 0);
+      mbar_wait(smem_u32(&bars->acc), 0);          // every MMA has completed: the stage buffers are free to reuse
       tc_fence_after();
     }
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    float* orow = nullptr;
-    if (row_ok) orow = (p.nsplit > 1) ? p.part + ((long long)z * p.M + m) * p.N + n0 : p.out + m * p.ldo + n0;
-    const float* rrow = (row_ok && p.res && p.nsplit == 1) ? p.res + m * p.ldr + n0 : nullptr;
-    for (int c0 = 0; c0 < un; c0 += 16) {
-      uint32_t acc[16];
+    constexpr int SLD = 36;                         // staging row stride in floats (conflict-free float4 access)
+    float* stg = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * SLD;
+    const bool final_out = p.nsplit == 1;
+    float* obase = final_out ? p.out : p.part + (long long)z * p.M * p.N;
+    const long long old = final_out ? p.ldo : (long long)p.N;
+    for (int c0 = 0; c0 < un; c0 += 32) {
+      const int cw = min(32, un - c0);              // 32 or 16 accumulator columns in this pass
+      uint32_t acc[32];
       if (n_iter > 0) {
         tmem_ld16(tmem + lane_base + c0, acc);
+        if (cw == 32) tmem_ld16(tmem + lane_base + c0 + 16, acc + 16);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0u;
+        for (int j = 0; j < 32; ++j) acc[j] = 0u;
       }
-      if (!row_ok) continue;
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const int c = c0 + j4 * 4;
-        if (c >= wn) break;
+      for (int j4 = 0; j4 < 8; ++j4) {
+        if (j4 * 4 >= cw) break;
         float o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float x = __uint_as_float(acc[j4 * 4 + j]);
-          if (p.nsplit == 1) {
-            if (p.bias && c + j < wn) x += p.bias[n0 + c + j];
+          const int c = c0 + j4 * 4 + j;
+          if (final_out) {
+            if (p.bias && c < wn) x += __ldg(p.bias + n0 + c);
             if (p.act == 1) x = gelu_erf(x);
           }
           o[j] = x;
         }
-        if (c + 3 < wn && p.vec_ok) {
-          if (rrow) { const float4 q = *reinterpret_cast<const float4*>(rrow + c); o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w; }
-          *reinterpret_cast<float4*>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-          for (int j = 0; j < 4 && c + j < wn; ++j) orow[c + j] = o[j] + (rrow ? rrow[c + j] : 0.f);
+        *reinterpret_cast<float4*>(stg + lane * SLD + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3), cc = (lane & 7) * 4;
+        const long long mm = (long long)tile_m * BM + warp * 32 + rr;
+        const int c = c0 + cc;
+        if (mm < p.M && cc < cw && c < wn) {
+          float4 v = *reinterpret_cast<const float4*>(stg + rr * SLD + cc);
+          float* op = obase + mm * old + n0 + c;
+          const float* rp = (final_out && p.res) ? p.res + mm * p.ldr + n0 + c : nullptr;
+          if (c + 3 < wn && p.vec_ok) {
+            if (rp) { const float4 q = *reinterpret_cast<const float4*>(rp); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+            *reinterpret_cast<float4*>(op) = v;
+          } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            for (int j = 0; j < 4 && c + j < wn; ++j) op[j] = vv[j] + (rp ? rp[j] : 0.f);
+          }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 4) {
     // -------------------------------- B loader --------------------------------

@@ -174,6 +174,9 @@ class Plan:
             c0.rowmap = _draw(k, perm_fn) if shuffle_orders else list(range(k))
             self.c_levels = [c0]
         n0 = level0()
+        if c_strides is not None:
+            n0._nbr = c0._nbr          # same points, same numbering: share the neighbour tables / tap masks
+
         n0.rowmap = _draw(k, perm_fn) if shuffle_orders else list(range(k))
         self.n_levels = [n0]
 
