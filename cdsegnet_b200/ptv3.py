@@ -97,18 +97,24 @@ class SubMConv3d(nn.Module):
 
 
 class _PackCache:
-    """packed tensor-core operand blocks, rebuilt when a source parameter / buffer changes"""
+    """packed tensor-core operand blocks, rebuilt when a source parameter / buffer changes.  Entries are keyed
+    by the owning parameter OBJECT (weak reference + identity check: `id()` alone is recycled by Python and the
+    CUDA caching allocator recycles data_ptr, so a dead model's entry must never match a new parameter)."""
 
     def __init__(self):
         self.c = {}
 
     def get(self, key, tensors, build):
+        import weakref
+        owner = tensors[0]
         sig = tuple((t._version, t.data_ptr()) for t in tensors if t is not None)
         e = self.c.get(key)
-        if e is None or e[0] != sig:
-            e = (sig, build())
+        if e is None or e[0]() is not owner or e[1] != sig:
+            if len(self.c) > 4096:                       # drop entries whose parameter died
+                self.c = {k: v for k, v in self.c.items() if v[0]() is not None}
+            e = (weakref.ref(owner), sig, build())
             self.c[key] = e
-        return e[1]
+        return e[2]
 
 
 _PACK = _PackCache()
