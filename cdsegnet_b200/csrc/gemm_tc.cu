@@ -26,11 +26,11 @@ namespace gt {
 constexpr int BM = 128;
 constexpr int NT = 128;                // max N tile (TMEM columns)
 constexpr int KC = 16;                 // fp32 elements per k-chunk (64 B per row)
-constexpr int STAGES = 2;
+constexpr int MAX_STAGES = 4;
 constexpr int NTHREADS = 192;
 constexpr int A_BYTES = BM * KC * 4;   // one of hi / lo
 constexpr int B_BYTES = NT * KC * 4;   // one of hi / lo (full tile; narrower tiles use a prefix)
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+// a stage holds A_hi | A_lo | B_hi | B_lo ; the B blocks are sized for this launch's widest N tile
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,15 +99,19 @@ struct Params {
   float* out; long long ldo;
   float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
   int vec_ok;                             // output / residual rows are 16-byte aligned
+  int stages, b_bytes, tmem_cols;         // pipeline depth (2..4), bytes of one B block (hi or lo), TMEM columns (pow2 >= 32)
 };
 
 struct Bars {
-  uint64_t full_a[STAGES], full_b[STAGES], empty[STAGES], acc;
+  uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES], acc;
   uint32_t tmem_slot, pad;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const int STAGES = p.stages;
+  const int B_BYTES = p.b_bytes;
+  const int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   Bars* bars = reinterpret_cast<Bars*>(smem + STAGES * STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x, tile_n = blockIdx.y, z = blockIdx.z;
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   }
   if (warp == 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)),
-                 "r"((uint32_t)NT)
+                 "r"((uint32_t)p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -140,10 +144,17 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
 
-  // number of (tap, k-chunk) iterations of this CTA -- identical in every role
-  int n_iter = 0;
-  for (int t = t_begin; t < t_end; ++t)
-    if ((mask >> (t & 31)) & 1u || p.T > 32) n_iter += kch;
+  // present taps of this CTA's split (identical in every role) -> iteration it = (tap taps[it / kch], chunk it % kch)
+  uint8_t taps[32];
+  int ntap = 0;
+  if (p.T <= 32) {
+    for (int t = t_begin; t < t_end; ++t)
+      if ((mask >> t) & 1u) taps[ntap++] = (uint8_t)t;
+  } else {
+    ntap = t_end - t_begin;
+  }
+  const int n_iter = ntap * kch;
+  auto tap_of = [&](int it) { const int j = it / kch; return p.T <= 32 ? (int)taps[j] : t_begin + j; };
 
   if (warp < 4) {
     // ------------------------------- A producers -------------------------------
@@ -151,34 +162,42 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
     const long long m = (long long)tile_m * BM + r;
     const bool row_ok = m < p.M;
     const uint32_t a_off = (uint32_t)((r >> 3) * (KC / 4) * 128 + (r & 7) * 16);
-    int it = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      if (!((mask >> (t & 31)) & 1u) && p.T <= 32) continue;
+    // software pipeline: the loads of iteration it+1 are in flight while iteration it is split and stored
+    auto fetch = [&](int it, float4* v) {
+      const int t = tap_of(it), kc = it - (it / kch) * kch;
       long long src = -1;
-      if (row_ok) src = p.idx ? (long long)p.idx[m * p.T + t] : m;
-      // without idx, "tap" t is the t-th K-slice of the same row (split-K of a plain Linear)
-      const float4* row = src >= 0 ? reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) : nullptr;
-      for (int kc = 0; kc < kch; ++kc, ++it) {
-        const int s = it % STAGES, u = it / STAGES;
-        float4 v[KC / 4];
+      if (row_ok) src = p.idx ? (long long)__ldg(p.idx + m * p.T + t) : m;
+      if (src >= 0) {
+        const float4* row = reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) + kc * (KC / 4);
 #pragma unroll
-        for (int j = 0; j < KC / 4; ++j) v[j] = row ? __ldg(row + kc * (KC / 4) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
-        uint8_t* hi = smem + s * STAGE_BYTES + a_off;
-        uint8_t* lo = hi + A_BYTES;
+        for (int j = 0; j < KC / 4; ++j) v[j] = __ldg(row + j);
+      } else {
 #pragma unroll
-        for (int j = 0; j < KC / 4; ++j) {
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u); l.x = v[j].x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u); l.y = v[j].y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u); l.z = v[j].z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u); l.w = v[j].w - h.w;
-          *reinterpret_cast<float4*>(hi + j * 128) = h;
-          *reinterpret_cast<float4*>(lo + j * 128) = l;
-        }
-        fence_async_smem();
-        mbar_arrive(smem_u32(&bars->full_a[s]));
+        for (int j = 0; j < KC / 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    float4 va[KC / 4], vb[KC / 4];
+    if (n_iter > 0) fetch(0, va);
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % STAGES, u = it / STAGES;
+      if (it + 1 < n_iter) fetch(it + 1, vb);
+      if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
+      uint8_t* hi = smem + s * STAGE_BYTES + a_off;
+      uint8_t* lo = hi + A_BYTES;
+#pragma unroll
+      for (int j = 0; j < KC / 4; ++j) {
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(va[j].x) & 0xFFFFE000u); l.x = va[j].x - h.x;
+        h.y = __uint_as_float(__float_as_uint(va[j].y) & 0xFFFFE000u); l.y = va[j].y - h.y;
+        h.z = __uint_as_float(__float_as_uint(va[j].z) & 0xFFFFE000u); l.z = va[j].z - h.z;
+        h.w = __uint_as_float(__float_as_uint(va[j].w) & 0xFFFFE000u); l.w = va[j].w - h.w;
+        *reinterpret_cast<float4*>(hi + j * 128) = h;
+        *reinterpret_cast<float4*>(lo + j * 128) = l;
+      }
+      fence_async_smem();
+      mbar_arrive(smem_u32(&bars->full_a[s]));
+#pragma unroll
+      for (int j = 0; j < KC / 4; ++j) va[j] = vb[j];
     }
     // --------------------------------- epilogue ---------------------------------
     // TMEM (lane == row) -> registers -> bias/GELU -> shared-memory staging (each warp only touches its own
@@ -245,18 +264,15 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
     // -------------------------------- B loader --------------------------------
     if (lane == 0) {
       const uint32_t bbytes = (uint32_t)un * KC * 4;            // prefix of the hi / lo block (n-groups are outermost)
-      int it = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        if (!((mask >> (t & 31)) & 1u) && p.T <= 32) continue;
-        for (int kc = 0; kc < kch; ++kc, ++it) {
-          const int s = it % STAGES, u = it / STAGES;
-          if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
-          const float* blk = p.Bp + ((((long long)t * kch + kc) * ntiles + tile_n) * 2) * (NT * KC);
-          uint8_t* b_hi = smem + s * STAGE_BYTES + 2 * A_BYTES;
-          mbar_expect_tx(smem_u32(&bars->full_b[s]), 2 * bbytes);
-          tma_load_1d(smem_u32(b_hi), blk, bbytes, smem_u32(&bars->full_b[s]));
-          tma_load_1d(smem_u32(b_hi + B_BYTES), blk + NT * KC, bbytes, smem_u32(&bars->full_b[s]));
-        }
+      for (int it = 0; it < n_iter; ++it) {
+        const int t = tap_of(it), kc = it - (it / kch) * kch;
+        const int s = it % STAGES, u = it / STAGES;
+        if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
+        const float* blk = p.Bp + ((((long long)t * kch + kc) * ntiles + tile_n) * 2) * (NT * KC);
+        uint8_t* b_hi = smem + s * STAGE_BYTES + 2 * A_BYTES;
+        mbar_expect_tx(smem_u32(&bars->full_b[s]), 2 * bbytes);
+        tma_load_1d(smem_u32(b_hi), blk, bbytes, smem_u32(&bars->full_b[s]));
+        tma_load_1d(smem_u32(b_hi + B_BYTES), blk + NT * KC, bbytes, smem_u32(&bars->full_b[s]));
       }
     }
   } else {
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)NT) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -386,17 +402,27 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
     return CDSEG_EINVAL;
   if (M == 0) return CDSEG_OK;
   if (workspace_bytes < cdseg_gemm_tc_workspace_bytes(M, N, nsplit)) return CDSEG_ENOSPC;
-  const size_t smem = (size_t)gt::STAGES * gt::STAGE_BYTES + sizeof(gt::Bars) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  const int un_max = N >= gt::NT ? gt::NT : ((N + 15) & ~15);
+  const int b_bytes = un_max * gt::KC * 4;
+  const int stage_bytes = 2 * gt::A_BYTES + 2 * b_bytes;
+  const int iters = (int)((long long)T * (K / gt::KC) / nsplit);      // upper bound of k-iterations per CTA
+  int stages = iters >= 12 ? 4 : (iters >= 4 ? 3 : 2);
+  const size_t cap = iters >= 12 ? 100 * 1024 : 72 * 1024;             // deep K loops: 2 CTAs/SM with a deeper ring, else >= 3 CTAs/SM
+  while (stages > 2 && (size_t)stages * stage_bytes > cap) --stages;
+  // the epilogue stages 4 warps x 32 rows x 36 floats through the (by then idle) stage buffers
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(gt::Bars) + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(gt::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured = smem;
   }
   gt::Params p;
   p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp;
   p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.ldr = ldr; p.act = act; p.out = out; p.ldo = ldo;
   p.part = (float*)workspace; p.nsplit = nsplit;
+  p.stages = stages; p.b_bytes = b_bytes;
+  p.tmem_cols = un_max <= 32 ? 32 : (un_max <= 64 ? 64 : 128);
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + gt::NT - 1) / gt::NT, nsplit);
