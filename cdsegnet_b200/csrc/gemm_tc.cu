@@ -17,7 +17,7 @@
 //              (TMEM lane == row): + bias, GELU, + residual, fp32 rows to HBM
 //   warp 4     B loader: one TMA bulk copy per k-chunk of the pre-split, pre-tiled weight block
 //   warp 5     MMA issuer: 6 x tcgen05.mma (M128 x N x K8) per k-chunk, commit -> frees the stage
-// 2-stage mbarrier ring, 3 CTAs per SM; taps that no row of the tile has are skipped via a per-tile tap mask;
+// asynchronous (cp.async) gather ring for A, TMA ring for B; taps that no row of the tile has are skipped via a per-tile tap mask;
 // optional split over taps (grid.z) for levels with few rows (partials reduced by a second kernel).
 #include "common.cuh"
 
@@ -26,7 +26,6 @@ namespace gt {
 constexpr int BM = 128;
 constexpr int NT = 128;                // max N tile (TMEM columns)
 constexpr int KC = 16;                 // fp32 elements per k-chunk (64 B per row)
-constexpr int MAX_STAGES = 4;
 constexpr int NTHREADS = 192;
 constexpr int A_BYTES = BM * KC * 4;   // one of hi / lo
 constexpr int B_BYTES = NT * KC * 4;   // one of hi / lo (full tile; narrower tiles use a prefix)
@@ -99,20 +98,35 @@ struct Params {
   float* out; long long ldo;
   float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
   int vec_ok;                             // output / residual rows are 16-byte aligned
-  int stages, b_bytes, tmem_cols;         // pipeline depth (2..4), bytes of one B block (hi or lo), TMEM columns (pow2 >= 32)
+  int R, SB, b_bytes, tmem_cols;          // raw-A ring depth, B ring depth, bytes of one B block (hi or lo), TMEM columns
 };
 
+constexpr int MAX_RING = 8;
+constexpr int LO_RING = 2;
+
 struct Bars {
-  uint64_t full_a[MAX_STAGES], full_b[MAX_STAGES], empty[MAX_STAGES], acc;
+  uint64_t full_a[MAX_RING], empty_raw[MAX_RING], full_b[MAX_RING], empty_b[MAX_RING], empty_lo[LO_RING], acc;
   uint32_t tmem_slot, pad;
 };
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// shared memory: [raw ring: R x 8 KB][lo ring: 2 x 8 KB][B ring: SB x (hi|lo)][barriers]
+//  * raw slot: the fp32 A tile exactly as gathered (cp.async, 16-byte pieces placed in the UMMA K-major core-matrix
+//    layout); the producer truncates it IN PLACE to its TF32 "hi" part and writes the residual "lo" tile
+//  * up to R-1 gathers are in flight per thread without holding registers (the conv is gather-latency bound)
 __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int STAGES = p.stages;
-  const int B_BYTES = p.b_bytes;
-  const int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  Bars* bars = reinterpret_cast<Bars*>(smem + STAGES * STAGE_BYTES);
+  const int R = p.R, SB = p.SB, B_BYTES = p.b_bytes;
+  uint8_t* s_raw = smem;
+  uint8_t* s_lo = s_raw + R * A_BYTES;
+  uint8_t* s_b = s_lo + LO_RING * A_BYTES;
+  Bars* bars = reinterpret_cast<Bars*>(s_b + (size_t)SB * 2 * B_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x, tile_n = blockIdx.y, z = blockIdx.z;
   const int ntiles = (p.N + NT - 1) / NT;
@@ -120,16 +134,17 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   const int wn = min(NT, p.N - n0);                 // valid output columns of this tile
   const int un = (wn + 15) & ~15;                   // UMMA N (multiple of 16)
   const int kch = p.K / KC;
-  // taps handled by this split
   const int t_begin = (int)((long long)p.T * z / p.nsplit), t_end = (int)((long long)p.T * (z + 1) / p.nsplit);
   const uint32_t mask = p.tile_mask ? p.tile_mask[tile_m] : 0xffffffffu;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAX_RING; ++s) {
       mbar_init(smem_u32(&bars->full_a[s]), 128);
+      mbar_init(smem_u32(&bars->empty_raw[s]), 1);
       mbar_init(smem_u32(&bars->full_b[s]), 1);
-      mbar_init(smem_u32(&bars->empty[s]), 1);
+      mbar_init(smem_u32(&bars->empty_b[s]), 1);
     }
+    for (int s = 0; s < LO_RING; ++s) mbar_init(smem_u32(&bars->empty_lo[s]), 1);
     mbar_init(smem_u32(&bars->acc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -162,53 +177,64 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
     const long long m = (long long)tile_m * BM + r;
     const bool row_ok = m < p.M;
     const uint32_t a_off = (uint32_t)((r >> 3) * (KC / 4) * 128 + (r & 7) * 16);
-    // software pipeline: the loads of iteration it+1 are in flight while iteration it is split and stored
-    auto fetch = [&](int it, float4* v) {
-      const int t = tap_of(it), kc = it - (it / kch) * kch;
+    const int D = R - 2;                              // gathers in flight per thread (>= 0)
+    auto issue = [&](int j) {                         // asynchronous gather of iteration j into raw slot j % R
+      const int q = j % R, u = j / R;
+      if (u > 0) mbar_wait(smem_u32(&bars->empty_raw[q]), (uint32_t)((u - 1) & 1));
+      const int t = tap_of(j), kc = j - (j / kch) * kch;
       long long src = -1;
       if (row_ok) src = p.idx ? (long long)__ldg(p.idx + m * p.T + t) : m;
-      if (src >= 0) {
-        const float4* row = reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) + kc * (KC / 4);
+      const float* row = src >= 0 ? p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K) + kc * KC : p.A;
+      const uint32_t nbytes = src >= 0 ? 16u : 0u;    // src-size 0 => the 16 bytes are zero-filled
+      const uint32_t dst = smem_u32(s_raw + q * A_BYTES + a_off);
 #pragma unroll
-        for (int j = 0; j < KC / 4; ++j) v[j] = __ldg(row + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < KC / 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int c = 0; c < KC / 4; ++c) cp_async16(dst + c * 128, row + c * 4, nbytes);
     };
-    float4 va[KC / 4], vb[KC / 4];
-    if (n_iter > 0) fetch(0, va);
+    for (int j = 0; j < D; ++j) {
+      if (j < n_iter) issue(j);
+      cp_async_commit();
+    }
     for (int it = 0; it < n_iter; ++it) {
-      const int s = it % STAGES, u = it / STAGES;
-      if (it + 1 < n_iter) fetch(it + 1, vb);
-      if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
-      uint8_t* hi = smem + s * STAGE_BYTES + a_off;
-      uint8_t* lo = hi + A_BYTES;
+      if (it + D < n_iter) issue(it + D);
+      cp_async_commit();
+      // all but the newest D groups are complete  =>  this thread's pieces of iteration `it` have landed
+      switch (D) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        default: cp_async_wait<6>(); break;
+      }
+      const int q = it % R, l = it % LO_RING, ul = it / LO_RING;
+      if (ul > 0) mbar_wait(smem_u32(&bars->empty_lo[l]), (uint32_t)((ul - 1) & 1));
+      uint8_t* hi = s_raw + q * A_BYTES + a_off;      // each thread only touches the pieces it gathered itself
+      uint8_t* lo = s_lo + l * A_BYTES + a_off;
 #pragma unroll
-      for (int j = 0; j < KC / 4; ++j) {
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(va[j].x) & 0xFFFFE000u); l.x = va[j].x - h.x;
-        h.y = __uint_as_float(__float_as_uint(va[j].y) & 0xFFFFE000u); l.y = va[j].y - h.y;
-        h.z = __uint_as_float(__float_as_uint(va[j].z) & 0xFFFFE000u); l.z = va[j].z - h.z;
-        h.w = __uint_as_float(__float_as_uint(va[j].w) & 0xFFFFE000u); l.w = va[j].w - h.w;
-        *reinterpret_cast<float4*>(hi + j * 128) = h;
-        *reinterpret_cast<float4*>(lo + j * 128) = l;
+      for (int c = 0; c < KC / 4; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(hi + c * 128);
+        float4 h, w;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); w.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); w.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); w.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); w.w = v.w - h.w;
+        *reinterpret_cast<float4*>(hi + c * 128) = h;
+        *reinterpret_cast<float4*>(lo + c * 128) = w;
       }
       fence_async_smem();
-      mbar_arrive(smem_u32(&bars->full_a[s]));
-#pragma unroll
-      for (int j = 0; j < KC / 4; ++j) va[j] = vb[j];
+      mbar_arrive(smem_u32(&bars->full_a[q]));
     }
     // --------------------------------- epilogue ---------------------------------
     // TMEM (lane == row) -> registers -> bias/GELU -> shared-memory staging (each warp only touches its own
     // 32 rows, so __syncwarp suffices) -> coalesced 128-byte row segments to HBM (+ residual, read coalesced).
     if (n_iter > 0) {
-      mbar_wait(smem_u32(&bars->acc), 0);          // every MMA has completed: the stage buffers are free to reuse
+      mbar_wait(smem_u32(&bars->acc), 0);          // every MMA has completed: the rings are free to reuse
       tc_fence_after();
     }
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     constexpr int SLD = 36;                         // staging row stride in floats (conflict-free float4 access)
-    float* stg = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * SLD;
+    float* stg = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * SLD;     // 18 KB <= raw + lo rings (>= 32 KB)
     const bool final_out = p.nsplit == 1;
     float* obase = final_out ? p.out : p.part + (long long)z * p.M * p.N;
     const long long old = final_out ? p.ldo : (long long)p.N;
@@ -253,8 +279,10 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
             if (rp) { const float4 q = *reinterpret_cast<const float4*>(rp); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
             *reinterpret_cast<float4*>(op) = v;
           } else {
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-            for (int j = 0; j < 4 && c + j < wn; ++j) op[j] = vv[j] + (rp ? rp[j] : 0.f);
+            if (c + 0 < wn) op[0] = v.x + (rp ? rp[0] : 0.f);
+            if (c + 1 < wn) op[1] = v.y + (rp ? rp[1] : 0.f);
+            if (c + 2 < wn) op[2] = v.z + (rp ? rp[2] : 0.f);
+            if (c + 3 < wn) op[3] = v.w + (rp ? rp[3] : 0.f);
           }
         }
       }
@@ -266,10 +294,10 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       const uint32_t bbytes = (uint32_t)un * KC * 4;            // prefix of the hi / lo block (n-groups are outermost)
       for (int it = 0; it < n_iter; ++it) {
         const int t = tap_of(it), kc = it - (it / kch) * kch;
-        const int s = it % STAGES, u = it / STAGES;
-        if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
+        const int s = it % SB, u = it / SB;
+        if (u > 0) mbar_wait(smem_u32(&bars->empty_b[s]), (uint32_t)((u - 1) & 1));
         const float* blk = p.Bp + ((((long long)t * kch + kc) * ntiles + tile_n) * 2) * (NT * KC);
-        uint8_t* b_hi = smem + s * STAGE_BYTES + 2 * A_BYTES;
+        uint8_t* b_hi = s_b + (size_t)s * 2 * B_BYTES;
         mbar_expect_tx(smem_u32(&bars->full_b[s]), 2 * bbytes);
         tma_load_1d(smem_u32(b_hi), blk, bbytes, smem_u32(&bars->full_b[s]));
         tma_load_1d(smem_u32(b_hi + B_BYTES), blk + NT * KC, bbytes, smem_u32(&bars->full_b[s]));
@@ -281,12 +309,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       // kind::tf32: D fp32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(un >> 3) << 17) | ((128u >> 4) << 24);
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it % STAGES, u = it / STAGES;
-        mbar_wait(smem_u32(&bars->full_a[s]), (uint32_t)(u & 1));
-        mbar_wait(smem_u32(&bars->full_b[s]), (uint32_t)(u & 1));
+        const int q = it % R, l = it % LO_RING, s = it % SB;
+        mbar_wait(smem_u32(&bars->full_a[q]), (uint32_t)((it / R) & 1));
+        mbar_wait(smem_u32(&bars->full_b[s]), (uint32_t)((it / SB) & 1));
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint32_t a_hi = smem_u32(s_raw + q * A_BYTES), a_lo = smem_u32(s_lo + l * A_BYTES);
+        const uint32_t b_hi = smem_u32(s_b + (size_t)s * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
 #pragma unroll
         for (int ks = 0; ks < KC / 8; ++ks) {                    // K = 8 per MMA = 2 core matrices = 256 B
           const uint64_t ah = make_desc(a_hi + ks * 256, 128, (KC / 4) * 128), al = make_desc(a_lo + ks * 256, 128, (KC / 4) * 128);
@@ -295,7 +323,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
           umma_tf32(tmem, ah, bl, idesc, 1);
           umma_tf32(tmem, ah, bh, idesc, 1);
         }
-        umma_commit(smem_u32(&bars->empty[s]));
+        umma_commit(smem_u32(&bars->empty_raw[q]));              // each commit tracks every MMA issued so far
+        umma_commit(smem_u32(&bars->empty_lo[l]));
+        umma_commit(smem_u32(&bars->empty_b[s]));
       }
       umma_commit(smem_u32(&bars->acc));
     }
@@ -404,13 +434,14 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   if (workspace_bytes < cdseg_gemm_tc_workspace_bytes(M, N, nsplit)) return CDSEG_ENOSPC;
   const int un_max = N >= gt::NT ? gt::NT : ((N + 15) & ~15);
   const int b_bytes = un_max * gt::KC * 4;
-  const int stage_bytes = 2 * gt::A_BYTES + 2 * b_bytes;
   const int iters = (int)((long long)T * (K / gt::KC) / nsplit);      // upper bound of k-iterations per CTA
-  int stages = iters >= 12 ? 4 : (iters >= 4 ? 3 : 2);
-  const size_t cap = iters >= 12 ? 100 * 1024 : 72 * 1024;             // deep K loops: 2 CTAs/SM with a deeper ring, else >= 3 CTAs/SM
-  while (stages > 2 && (size_t)stages * stage_bytes > cap) --stages;
-  // the epilogue stages 4 warps x 32 rows x 36 floats through the (by then idle) stage buffers
-  const size_t smem = (size_t)stages * stage_bytes + sizeof(gt::Bars) + 1024;
+  // ring depths: deep raw-A ring for gather-latency-bound K loops, shallow (more CTAs per SM) for 1-2 iteration GEMMs
+  int R = iters >= 12 ? 6 : (iters >= 4 ? 4 : 2);
+  int SB = iters >= 4 ? (un_max <= 32 ? 4 : (un_max <= 64 ? 3 : 2)) : 2;
+  auto smem_of = [&](int r, int sb) { return (size_t)(r + gt::LO_RING) * gt::A_BYTES + (size_t)sb * 2 * b_bytes + sizeof(gt::Bars) + 1024; };
+  const size_t cap = iters >= 12 ? 100 * 1024 : 74 * 1024;              // 2 CTAs/SM with a deep ring, else 3 CTAs/SM
+  while (R > 2 && smem_of(R, SB) > cap) --R;
+  const size_t smem = smem_of(R, SB);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(gt::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -421,7 +452,7 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp;
   p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.ldr = ldr; p.act = act; p.out = out; p.ldo = ldo;
   p.part = (float*)workspace; p.nsplit = nsplit;
-  p.stages = stages; p.b_bytes = b_bytes;
+  p.R = R; p.SB = SB; p.b_bytes = b_bytes;
   p.tmem_cols = un_max <= 32 ? 32 : (un_max <= 64 ? 64 : 128);
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
