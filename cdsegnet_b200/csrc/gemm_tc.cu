@@ -12,12 +12,12 @@
 // rate instead of the CUDA-core SGEMM / SIMT gather-GEMM this kernel replaces.
 //
 // CTA = 128 output rows x one N tile (<= 128 columns), 192 threads:
-//   warps 0-3  A producers (thread == row): gather 64 B of the row per k-chunk, split hi/lo, store to
-//              shared memory in the UMMA K-major core-matrix layout; afterwards the epilogue
+//   warps 0-3  A producers (thread == row == TMEM lane): gather 64 B of the row per k-chunk, split hi/lo, store
+//              both into tensor memory (the A operand never touches shared memory); afterwards the epilogue
 //              (TMEM lane == row): + bias, GELU, + residual, fp32 rows to HBM
 //   warp 4     B loader: one TMA bulk copy per k-chunk of the pre-split, pre-tiled weight block
 //   warp 5     MMA issuer: 6 x tcgen05.mma (M128 x N x K8) per k-chunk, commit -> frees the stage
-// asynchronous (cp.async) gather ring for A, TMA ring for B; taps that no row of the tile has are skipped via a per-tile tap mask;
+// A ring in TENSOR MEMORY (tcgen05.st by the producers, TS-form MMA), TMA ring for B in shared memory; taps that no row of the tile has are skipped via a per-tile tap mask;
 // optional split over taps (grid.z) for levels with few rows (partials reduced by a second kernel).
 #include "common.cuh"
 
@@ -98,34 +98,42 @@ struct Params {
   float* out; long long ldo;
   float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
   int vec_ok;                             // output / residual rows are 16-byte aligned
-  int R, SB, b_bytes, tmem_cols;          // raw-A ring depth, B ring depth, bytes of one B block (hi or lo), TMEM columns
+  int AT, SB, b_bytes, acc_cols, tmem_cols;   // A ring slots (TMEM), B ring stages (smem), bytes of one B block, TMEM layout
 };
 
-constexpr int MAX_RING = 8;
-constexpr int LO_RING = 2;
+constexpr int MAX_RING = 4;
+constexpr int STG_BYTES = 4 * 32 * 36 * 4;   // epilogue staging: 4 warps x 32 rows x 36 floats
 
 struct Bars {
-  uint64_t full_a[MAX_RING], empty_raw[MAX_RING], full_b[MAX_RING], empty_b[MAX_RING], empty_lo[LO_RING], acc;
+  uint64_t full_a[MAX_RING], empty_a[MAX_RING], full_b[MAX_RING], empty_b[MAX_RING], acc;
   uint32_t tmem_slot, pad;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+// D[tmem] (+)= A[tmem] . B[smem]   (A: lane = row, one 32-bit column per K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// shared memory: [raw ring: R x 8 KB][lo ring: 2 x 8 KB][B ring: SB x (hi|lo)][barriers]
-//  * raw slot: the fp32 A tile exactly as gathered (cp.async, 16-byte pieces placed in the UMMA K-major core-matrix
-//    layout); the producer truncates it IN PLACE to its TF32 "hi" part and writes the residual "lo" tile
-//  * up to R-1 gathers are in flight per thread without holding registers (the conv is gather-latency bound)
+// The A operand never touches shared memory: each producer thread gathers its row (prefetched one iteration
+// ahead in registers), splits it into TF32 hi / lo and stores both straight into TENSOR MEMORY (lane == row),
+// from where tcgen05.mma reads it (TS form).  With N as small as 32 an smem-resident A tile would be re-read by
+// all six MMAs of a k-chunk and the kernel became shared-memory-bandwidth bound (measured: 143 us -> see profiles/).
 __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int R = p.R, SB = p.SB, B_BYTES = p.b_bytes;
-  uint8_t* s_raw = smem;
-  uint8_t* s_lo = s_raw + R * A_BYTES;
-  uint8_t* s_b = s_lo + LO_RING * A_BYTES;
+  const int AT = p.AT, SB = p.SB, B_BYTES = p.b_bytes;
+  uint8_t* s_stg = smem;
+  uint8_t* s_b = smem + STG_BYTES;
   Bars* bars = reinterpret_cast<Bars*>(s_b + (size_t)SB * 2 * B_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x, tile_n = blockIdx.y, z = blockIdx.z;
@@ -140,11 +148,10 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_RING; ++s) {
       mbar_init(smem_u32(&bars->full_a[s]), 128);
-      mbar_init(smem_u32(&bars->empty_raw[s]), 1);
+      mbar_init(smem_u32(&bars->empty_a[s]), 1);
       mbar_init(smem_u32(&bars->full_b[s]), 1);
       mbar_init(smem_u32(&bars->empty_b[s]), 1);
     }
-    for (int s = 0; s < LO_RING; ++s) mbar_init(smem_u32(&bars->empty_lo[s]), 1);
     mbar_init(smem_u32(&bars->acc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -158,6 +165,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
+  const uint32_t tmem_a = tmem + (uint32_t)p.acc_cols;          // A ring: slot q at +32q : [hi 16 cols | lo 16 cols]
 
   // present taps of this CTA's split (identical in every role) -> iteration it = (tap taps[it / kch], chunk it % kch)
   uint8_t taps[32];
@@ -176,65 +184,57 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
     const int r = threadIdx.x;
     const long long m = (long long)tile_m * BM + r;
     const bool row_ok = m < p.M;
-    const uint32_t a_off = (uint32_t)((r >> 3) * (KC / 4) * 128 + (r & 7) * 16);
-    const int D = R - 2;                              // gathers in flight per thread (>= 0)
-    auto issue = [&](int j) {                         // asynchronous gather of iteration j into raw slot j % R
-      const int q = j % R, u = j / R;
-      if (u > 0) mbar_wait(smem_u32(&bars->empty_raw[q]), (uint32_t)((u - 1) & 1));
-      const int t = tap_of(j), kc = j - (j / kch) * kch;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    auto fetch = [&](int it, float4* v) {
+      const int t = tap_of(it), kc = it - (it / kch) * kch;
       long long src = -1;
       if (row_ok) src = p.idx ? (long long)__ldg(p.idx + m * p.T + t) : m;
-      const float* row = src >= 0 ? p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K) + kc * KC : p.A;
-      const uint32_t nbytes = src >= 0 ? 16u : 0u;    // src-size 0 => the 16 bytes are zero-filled
-      const uint32_t dst = smem_u32(s_raw + q * A_BYTES + a_off);
+      if (src >= 0) {
+        const float4* row = reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) + kc * (KC / 4);
 #pragma unroll
-      for (int c = 0; c < KC / 4; ++c) cp_async16(dst + c * 128, row + c * 4, nbytes);
+        for (int j = 0; j < KC / 4; ++j) v[j] = __ldg(row + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < KC / 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
-    for (int j = 0; j < D; ++j) {
-      if (j < n_iter) issue(j);
-      cp_async_commit();
-    }
+    float4 va[KC / 4], vb[KC / 4];
+    if (n_iter > 0) fetch(0, va);
     for (int it = 0; it < n_iter; ++it) {
-      if (it + D < n_iter) issue(it + D);
-      cp_async_commit();
-      // all but the newest D groups are complete  =>  this thread's pieces of iteration `it` have landed
-      switch (D) {
-        case 0: cp_async_wait<0>(); break;
-        case 1: cp_async_wait<1>(); break;
-        case 2: cp_async_wait<2>(); break;
-        case 3: cp_async_wait<3>(); break;
-        case 4: cp_async_wait<4>(); break;
-        case 5: cp_async_wait<5>(); break;
-        default: cp_async_wait<6>(); break;
-      }
-      const int q = it % R, l = it % LO_RING, ul = it / LO_RING;
-      if (ul > 0) mbar_wait(smem_u32(&bars->empty_lo[l]), (uint32_t)((ul - 1) & 1));
-      uint8_t* hi = s_raw + q * A_BYTES + a_off;      // each thread only touches the pieces it gathered itself
-      uint8_t* lo = s_lo + l * A_BYTES + a_off;
+      const int q = it % AT, u = it / AT;
+      if (it + 1 < n_iter) fetch(it + 1, vb);                    // next gather in flight while this one is split/stored
+      uint32_t hi[KC], lo[KC];
 #pragma unroll
-      for (int c = 0; c < KC / 4; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(hi + c * 128);
-        float4 h, w;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); w.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); w.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); w.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); w.w = v.w - h.w;
-        *reinterpret_cast<float4*>(hi + c * 128) = h;
-        *reinterpret_cast<float4*>(lo + c * 128) = w;
+      for (int j = 0; j < KC / 4; ++j) {
+        const float x[4] = {va[j].x, va[j].y, va[j].z, va[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
+          hi[j * 4 + e] = h;
+          lo[j * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
+        }
       }
-      fence_async_smem();
+      if (u > 0) {
+        mbar_wait(smem_u32(&bars->empty_a[q]), (uint32_t)((u - 1) & 1));
+        tc_fence_after();
+      }
+      tmem_st16(tmem_a + lane_base + q * 32, hi);
+      tmem_st16(tmem_a + lane_base + q * 32 + 16, lo);
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(smem_u32(&bars->full_a[q]));
+#pragma unroll
+      for (int j = 0; j < KC / 4; ++j) va[j] = vb[j];
     }
     // --------------------------------- epilogue ---------------------------------
     // TMEM (lane == row) -> registers -> bias/GELU -> shared-memory staging (each warp only touches its own
     // 32 rows, so __syncwarp suffices) -> coalesced 128-byte row segments to HBM (+ residual, read coalesced).
     if (n_iter > 0) {
-      mbar_wait(smem_u32(&bars->acc), 0);          // every MMA has completed: the rings are free to reuse
+      mbar_wait(smem_u32(&bars->acc), 0);
       tc_fence_after();
     }
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     constexpr int SLD = 36;                         // staging row stride in floats (conflict-free float4 access)
-    float* stg = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * SLD;     // 18 KB <= raw + lo rings (>= 32 KB)
+    float* stg = reinterpret_cast<float*>(s_stg) + (size_t)warp * 32 * SLD;
     const bool final_out = p.nsplit == 1;
     float* obase = final_out ? p.out : p.part + (long long)z * p.M * p.N;
     const long long old = final_out ? p.ldo : (long long)p.N;
@@ -309,22 +309,20 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       // kind::tf32: D fp32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(un >> 3) << 17) | ((128u >> 4) << 24);
       for (int it = 0; it < n_iter; ++it) {
-        const int q = it % R, l = it % LO_RING, s = it % SB;
-        mbar_wait(smem_u32(&bars->full_a[q]), (uint32_t)((it / R) & 1));
+        const int q = it % AT, s = it % SB;
+        mbar_wait(smem_u32(&bars->full_a[q]), (uint32_t)((it / AT) & 1));
         mbar_wait(smem_u32(&bars->full_b[s]), (uint32_t)((it / SB) & 1));
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(s_raw + q * A_BYTES), a_lo = smem_u32(s_lo + l * A_BYTES);
+        const uint32_t a_hi = tmem_a + q * 32, a_lo = a_hi + 16;
         const uint32_t b_hi = smem_u32(s_b + (size_t)s * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < KC / 8; ++ks) {                    // K = 8 per MMA = 2 core matrices = 256 B
-          const uint64_t ah = make_desc(a_hi + ks * 256, 128, (KC / 4) * 128), al = make_desc(a_lo + ks * 256, 128, (KC / 4) * 128);
+        for (int ks = 0; ks < KC / 8; ++ks) {                    // K = 8 per MMA: 8 TMEM columns of A, 2 core matrices (256 B) of B
           const uint64_t bh = make_desc(b_hi + ks * 256, 128, (KC / 4) * 128), bl = make_desc(b_lo + ks * 256, 128, (KC / 4) * 128);
-          umma_tf32(tmem, al, bh, idesc, (it | ks) != 0);        // small terms first
-          umma_tf32(tmem, ah, bl, idesc, 1);
-          umma_tf32(tmem, ah, bh, idesc, 1);
+          umma_tf32_ts(tmem, a_lo + ks * 8, bh, idesc, (it | ks) != 0);     // small terms first
+          umma_tf32_ts(tmem, a_hi + ks * 8, bl, idesc, 1);
+          umma_tf32_ts(tmem, a_hi + ks * 8, bh, idesc, 1);
         }
-        umma_commit(smem_u32(&bars->empty_raw[q]));              // each commit tracks every MMA issued so far
-        umma_commit(smem_u32(&bars->empty_lo[l]));
+        umma_commit(smem_u32(&bars->empty_a[q]));                // each commit tracks every MMA issued so far
         umma_commit(smem_u32(&bars->empty_b[s]));
       }
       umma_commit(smem_u32(&bars->acc));
@@ -435,13 +433,13 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   const int un_max = N >= gt::NT ? gt::NT : ((N + 15) & ~15);
   const int b_bytes = un_max * gt::KC * 4;
   const int iters = (int)((long long)T * (K / gt::KC) / nsplit);      // upper bound of k-iterations per CTA
-  // ring depths: deep raw-A ring for gather-latency-bound K loops, shallow (more CTAs per SM) for 1-2 iteration GEMMs
-  int R = iters >= 12 ? 6 : (iters >= 4 ? 4 : 2);
-  int SB = iters >= 4 ? (un_max <= 32 ? 4 : (un_max <= 64 ? 3 : 2)) : 2;
-  auto smem_of = [&](int r, int sb) { return (size_t)(r + gt::LO_RING) * gt::A_BYTES + (size_t)sb * 2 * b_bytes + sizeof(gt::Bars) + 1024; };
-  const size_t cap = iters >= 12 ? 100 * 1024 : 74 * 1024;              // 2 CTAs/SM with a deep ring, else 3 CTAs/SM
-  while (R > 2 && smem_of(R, SB) > cap) --R;
-  const size_t smem = smem_of(R, SB);
+  // TMEM: accumulator columns + A ring (32 columns per slot); allocation must be a power of two >= 32
+  const int acc_cols = un_max <= 32 ? 32 : (un_max <= 64 ? 64 : 128);
+  const int AT = acc_cols == 128 ? 4 : ((iters >= 4 && acc_cols <= 32) ? 3 : 2);   // 32+96=128, 64+64=128, 128+128=256 columns
+  int tmem_cols = 32;
+  while (tmem_cols < acc_cols + AT * 32) tmem_cols <<= 1;
+  const int SB = iters >= 4 ? (un_max <= 64 ? 4 : 3) : 2;
+  const size_t smem = (size_t)gt::STG_BYTES + (size_t)SB * 2 * b_bytes + sizeof(gt::Bars) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(gt::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -452,8 +450,7 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp;
   p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.ldr = ldr; p.act = act; p.out = out; p.ldo = ldo;
   p.part = (float*)workspace; p.nsplit = nsplit;
-  p.R = R; p.SB = SB; p.b_bytes = b_bytes;
-  p.tmem_cols = un_max <= 32 ? 32 : (un_max <= 64 ? 64 : 128);
+  p.AT = AT; p.SB = SB; p.b_bytes = b_bytes; p.acc_cols = acc_cols; p.tmem_cols = tmem_cols;
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + gt::NT - 1) / gt::NT, nsplit);
