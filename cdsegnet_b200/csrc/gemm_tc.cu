@@ -43,16 +43,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(done)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
+  if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
-  while (!done) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done)
-                 : "r"(bar), "r"(parity)
-                 : "memory");
-    if (!done && clock64() - t0 > WAIT_TIMEOUT_CYCLES) __trap();
-  }
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) __trap();       // a protocol bug must trap, never hang
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -185,10 +188,20 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
     const long long m = (long long)tile_m * BM + r;
     const bool row_ok = m < p.M;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // this tile's neighbour indices, staged once in shared memory (one coalesced block read) so that the per-tap
+    // row address no longer hangs off a dependent global load
+    int32_t* s_idx = reinterpret_cast<int32_t*>(s_b + (size_t)SB * 2 * B_BYTES + sizeof(Bars) + 64);
+    const bool idx_smem = p.idx != nullptr && p.T <= 32;
+    if (idx_smem) {
+      const long long base = (long long)tile_m * BM * p.T, total = (long long)p.M * p.T;
+      for (int j = r; j < BM * p.T; j += 128) s_idx[j] = base + j < total ? __ldg(p.idx + base + j) : -1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     auto fetch = [&](int it, float4* v) {
       const int t = tap_of(it), kc = it - (it / kch) * kch;
       long long src = -1;
-      if (row_ok) src = p.idx ? (long long)__ldg(p.idx + m * p.T + t) : m;
+      if (idx_smem) src = s_idx[r * p.T + t];
+      else if (row_ok) src = p.idx ? (long long)__ldg(p.idx + m * p.T + t) : m;
       if (src >= 0) {
         const float4* row = reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) + kc * (KC / 4);
 #pragma unroll
@@ -198,15 +211,14 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
         for (int j = 0; j < KC / 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    float4 va[KC / 4], vb[KC / 4];
-    if (n_iter > 0) fetch(0, va);
-    for (int it = 0; it < n_iter; ++it) {
+    // register ring of three gathers: iteration it+3 is requested right after iteration it has been stored, so
+    // every load has two full iterations to land (no register copies: the loop is unrolled by the ring size)
+    auto proc = [&](int it, float4* v) {
       const int q = it % AT, u = it / AT;
-      if (it + 1 < n_iter) fetch(it + 1, vb);                    // next gather in flight while this one is split/stored
       uint32_t hi[KC], lo[KC];
 #pragma unroll
       for (int j = 0; j < KC / 4; ++j) {
-        const float x[4] = {va[j].x, va[j].y, va[j].z, va[j].w};
+        const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
@@ -214,6 +226,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
           lo[j * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
         }
       }
+      if (it + 3 < n_iter) fetch(it + 3, v);
       if (u > 0) {
         mbar_wait(smem_u32(&bars->empty_a[q]), (uint32_t)((u - 1) & 1));
         tc_fence_after();
@@ -223,8 +236,15 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->full_a[q]));
-#pragma unroll
-      for (int j = 0; j < KC / 4; ++j) va[j] = vb[j];
+    };
+    float4 v0[KC / 4], v1[KC / 4], v2[KC / 4];
+    if (n_iter > 0) fetch(0, v0);
+    if (n_iter > 1) fetch(1, v1);
+    if (n_iter > 2) fetch(2, v2);
+    for (int it = 0; it < n_iter; it += 3) {
+      proc(it, v0);
+      if (it + 1 < n_iter) proc(it + 1, v1);
+      if (it + 2 < n_iter) proc(it + 2, v2);
     }
     // --------------------------------- epilogue ---------------------------------
     // TMEM (lane == row) -> registers -> bias/GELU -> shared-memory staging (each warp only touches its own
@@ -439,7 +459,8 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   int tmem_cols = 32;
   while (tmem_cols < acc_cols + AT * 32) tmem_cols <<= 1;
   const int SB = iters >= 4 ? (un_max <= 64 ? 4 : 3) : 2;
-  const size_t smem = (size_t)gt::STG_BYTES + (size_t)SB * 2 * b_bytes + sizeof(gt::Bars) + 1024;
+  const size_t smem = (size_t)gt::STG_BYTES + (size_t)SB * 2 * b_bytes + sizeof(gt::Bars) + 64 +
+                      ((idx && T <= 32) ? (size_t)gt::BM * T * 4 : 0) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(gt::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
