@@ -1,4 +1,4 @@
-// fp32-faithful GEMM on the 5th-gen tensor cores (tcgen05, kind::tf32, "3xTF32" split) with
+// fp32-faithful GEMM on the 5th-gen tensor cores (tcgen05, kind::f16, 3-term fp16 hi/lo split) with
 // (a) optionally GATHERED A rows -- the submanifold convolution as an implicit GEMM over taps --
 // and (b) a fused epilogue (bias, GELU, residual).  One kernel serves
 //   * spconv.SubMConv3d k=3 (ptv3.py:356-362, 1106-1123):  out[m] = b + sum_t in[nbr[m,t]] . W_t
@@ -6,10 +6,12 @@
 //     cross-attention q/kv/proj: ptv3.py:185-186, 311-313, 359, 458, 575-581, 911-913)
 // (ptv3.py = pointcept/models/point_transformer_v3/point_transformer_v3m1_base.py)
 //
-// Numerics: every fp32 operand x is split into hi = x & 0xFFFFE000 (exact TF32) and lo = x - hi;
-// acc += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo with fp32 accumulation in TMEM: relative error ~2^-21,
-// i.e. fp32-class results (the reference runs these layers in fp32 at inference), at tensor-core
-// rate instead of the CUDA-core SGEMM / SIMT gather-GEMM this kernel replaces.
+// Numerics: every fp32 operand x is split into hi = fp16(x) and lo = fp16(x - hi) (22 significant bits);
+// acc += A_lo.B_hi + A_hi.B_lo + A_hi.B_hi with fp32 accumulation in TMEM: relative error ~2^-21 per product,
+// i.e. fp32-class results (the reference runs these layers in fp32 at inference).  fp16 rather than TF32 halves
+// because ONE tcgen05.mma covers K=16 fp16 but only K=8 tf32, and the single issuing thread -- ~50 cycles per
+// tcgen05.mma regardless of N <= 64, measured in profiles/r01_microbench_mma_issue_latency.txt -- is what bounds
+// these skinny (N = 32..128) GEMMs.  Valid for |x| < 65504 (activations / weights of this network are O(1..100)).
 //
 // CTA = 128 output rows x one N tile (<= 128 columns), 192 threads:
 //   warps 0-3  A producers (thread == row == TMEM lane): gather 64 B of the row per k-chunk, split hi/lo, store
@@ -25,10 +27,8 @@ namespace gt {
 
 constexpr int BM = 128;
 constexpr int NT = 128;                // max N tile (TMEM columns)
-constexpr int KC = 16;                 // fp32 elements per k-chunk (64 B per row)
+constexpr int KC = 32;                 // fp32 elements per k-chunk (128 B per row) = 2 MMA K-steps of 16
 constexpr int NTHREADS = 192;
-constexpr int A_BYTES = BM * KC * 4;   // one of hi / lo
-constexpr int B_BYTES = NT * KC * 4;   // one of hi / lo (full tile; narrower tiles use a prefix)
 // a stage holds A_hi | A_lo | B_hi | B_lo ; the B blocks are sized for this launch's widest N tile
 constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;
 
@@ -112,10 +112,10 @@ struct Bars {
   uint32_t tmem_slot, pad;
 };
 
-// D[tmem] (+)= A[tmem] . B[smem]   (A: lane = row, one 32-bit column per K element)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]   (A: lane = row, two fp16 K elements per 32-bit column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem),
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   const int n0 = tile_n * NT;
   const int wn = min(NT, p.N - n0);                 // valid output columns of this tile
   const int un = (wn + 15) & ~15;                   // UMMA N (multiple of 16)
-  const int kch = p.K / KC;
+  const int kch = (p.K + KC - 1) / KC;
   const int t_begin = (int)((long long)p.T * z / p.nsplit), t_end = (int)((long long)p.T * (z + 1) / p.nsplit);
   const uint32_t mask = p.tile_mask ? p.tile_mask[tile_m] : 0xffffffffu;
 
@@ -202,31 +202,29 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       long long src = -1;
       if (idx_smem) src = s_idx[r * p.T + t];
       else if (row_ok) src = p.idx ? (long long)__ldg(p.idx + m * p.T + t) : m;
+      const int kleft = p.K - kc * KC;                                  // valid fp32 elements of this chunk (K may be 16 mod 32)
       if (src >= 0) {
         const float4* row = reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) + kc * (KC / 4);
 #pragma unroll
-        for (int j = 0; j < KC / 4; ++j) v[j] = __ldg(row + j);
+        for (int j = 0; j < KC / 4; ++j) v[j] = j * 4 < kleft ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
 #pragma unroll
         for (int j = 0; j < KC / 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    // register ring of three gathers: iteration it+3 is requested right after iteration it has been stored, so
-    // every load has two full iterations to land (no register copies: the loop is unrolled by the ring size)
+    // two gathers alternate in registers: iteration it+2 is requested right after iteration it has been stored
     auto proc = [&](int it, float4* v) {
       const int q = it % AT, u = it / AT;
-      uint32_t hi[KC], lo[KC];
+      uint32_t hi[KC / 2], lo[KC / 2];
 #pragma unroll
       for (int j = 0; j < KC / 4; ++j) {
-        const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
-          hi[j * 4 + e] = h;
-          lo[j * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
-        }
+        const __half2 h0 = __floats2half2_rn(v[j].x, v[j].y), h1 = __floats2half2_rn(v[j].z, v[j].w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(v[j].x - f0.x, v[j].y - f0.y), l1 = __floats2half2_rn(v[j].z - f1.x, v[j].w - f1.y);
+        hi[2 * j] = *reinterpret_cast<const uint32_t*>(&h0); hi[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        lo[2 * j] = *reinterpret_cast<const uint32_t*>(&l0); lo[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l1);
       }
-      if (it + 3 < n_iter) fetch(it + 3, v);
+      if (it + 2 < n_iter) fetch(it + 2, v);
       if (u > 0) {
         mbar_wait(smem_u32(&bars->empty_a[q]), (uint32_t)((u - 1) & 1));
         tc_fence_after();
@@ -237,14 +235,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->full_a[q]));
     };
-    float4 v0[KC / 4], v1[KC / 4], v2[KC / 4];
+    float4 v0[KC / 4], v1[KC / 4];
     if (n_iter > 0) fetch(0, v0);
     if (n_iter > 1) fetch(1, v1);
-    if (n_iter > 2) fetch(2, v2);
-    for (int it = 0; it < n_iter; it += 3) {
+    for (int it = 0; it < n_iter; it += 2) {
       proc(it, v0);
       if (it + 1 < n_iter) proc(it + 1, v1);
-      if (it + 2 < n_iter) proc(it + 2, v2);
     }
     // --------------------------------- epilogue ---------------------------------
     // TMEM (lane == row) -> registers -> bias/GELU -> shared-memory staging (each warp only touches its own
@@ -311,12 +307,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   } else if (warp == 4) {
     // -------------------------------- B loader --------------------------------
     if (lane == 0) {
-      const uint32_t bbytes = (uint32_t)un * KC * 4;            // prefix of the hi / lo block (n-groups are outermost)
+      const uint32_t bbytes = (uint32_t)un * KC * 2;            // prefix of the fp16 hi / lo block (n-groups are outermost)
       for (int it = 0; it < n_iter; ++it) {
         const int t = tap_of(it), kc = it - (it / kch) * kch;
         const int s = it % SB, u = it / SB;
         if (u > 0) mbar_wait(smem_u32(&bars->empty_b[s]), (uint32_t)((u - 1) & 1));
-        const float* blk = p.Bp + ((((long long)t * kch + kc) * ntiles + tile_n) * 2) * (NT * KC);
+        const __half* blk = reinterpret_cast<const __half*>(p.Bp) + ((((long long)t * kch + kc) * ntiles + tile_n) * 2) * (NT * KC);
         uint8_t* b_hi = s_b + (size_t)s * 2 * B_BYTES;
         mbar_expect_tx(smem_u32(&bars->full_b[s]), 2 * bbytes);
         tma_load_1d(smem_u32(b_hi), blk, bbytes, smem_u32(&bars->full_b[s]));
@@ -326,8 +322,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   } else {
     // ------------------------------- MMA issuer -------------------------------
     if (lane == 0 && n_iter > 0) {
-      // kind::tf32: D fp32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(un >> 3) << 17) | ((128u >> 4) << 24);
+      // kind::f16: D fp32 (1<<4), A = B = F16 (format 0), both K-major, N, M=128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(un >> 3) << 17) | ((128u >> 4) << 24);
       for (int it = 0; it < n_iter; ++it) {
         const int q = it % AT, s = it % SB;
         mbar_wait(smem_u32(&bars->full_a[q]), (uint32_t)((it / AT) & 1));
@@ -336,11 +332,11 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
         const uint32_t a_hi = tmem_a + q * 32, a_lo = a_hi + 16;
         const uint32_t b_hi = smem_u32(s_b + (size_t)s * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < KC / 8; ++ks) {                    // K = 8 per MMA: 8 TMEM columns of A, 2 core matrices (256 B) of B
-          const uint64_t bh = make_desc(b_hi + ks * 256, 128, (KC / 4) * 128), bl = make_desc(b_lo + ks * 256, 128, (KC / 4) * 128);
-          umma_tf32_ts(tmem, a_lo + ks * 8, bh, idesc, (it | ks) != 0);     // small terms first
-          umma_tf32_ts(tmem, a_hi + ks * 8, bl, idesc, 1);
-          umma_tf32_ts(tmem, a_hi + ks * 8, bh, idesc, 1);
+        for (int ks = 0; ks < KC / 16; ++ks) {                   // K = 16 per MMA: 8 TMEM columns of A, 2 core matrices (256 B) of B
+          const uint64_t bh = make_desc(b_hi + ks * 256, 128, (KC / 8) * 128), bl = make_desc(b_lo + ks * 256, 128, (KC / 8) * 128);
+          umma_f16_ts(tmem, a_lo + ks * 8, bh, idesc, (it | ks) != 0);     // small terms first
+          umma_f16_ts(tmem, a_hi + ks * 8, bl, idesc, 1);
+          umma_f16_ts(tmem, a_hi + ks * 8, bh, idesc, 1);
         }
         umma_commit(smem_u32(&bars->empty_a[q]));                // each commit tracks every MMA issued so far
         umma_commit(smem_u32(&bars->empty_b[s]));
@@ -388,38 +384,38 @@ __global__ void tile_mask_kernel(const int32_t* __restrict__ nbr, long long M, i
 }
 
 // pack W [T][K][N] (fp32, row-major: the tap-major transposed conv weight, or weight^T of a Linear) into
-// Bp [T][K/KC][ntiles][2][NT*KC]: K-major core-matrix tiles, hi then lo.
-__global__ void pack_b_kernel(const float* __restrict__ W, int T, int K, int N, float* __restrict__ Bp) {
-  const int ntiles = (N + NT - 1) / NT, kch = K / KC;
+// Bp [T][ceil(K/KC)][ntiles][2][NT*KC] fp16: K-major core-matrix tiles (8 n x 8 k), hi block then lo block; K padded with 0
+__global__ void pack_b_kernel(const float* __restrict__ W, int T, int K, int N, __half* __restrict__ Bp) {
+  const int ntiles = (N + NT - 1) / NT, kch = (K + KC - 1) / KC;
   const long long total = (long long)T * kch * ntiles * NT * KC;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  // destination element order inside a block: (n/8, k/4, n%8, k%4)
+  // destination element order inside a block: (n/8, k/8, n%8, k%8)
   const int e = (int)(i % (NT * KC));
   const long long blk = i / (NT * KC);
   const int tn = (int)(blk % ntiles);
   const int kc = (int)((blk / ntiles) % kch);
   const int t = (int)(blk / ((long long)ntiles * kch));
-  const int k4 = e % 4, n8 = (e / 4) % 8, kg = (e / 32) % (KC / 4), ng = e / (32 * (KC / 4));
-  const int n = tn * NT + ng * 8 + n8, k = kc * KC + kg * 4 + k4;
-  const float x = n < N ? W[((long long)t * K + k) * N + n] : 0.f;
-  const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  float* dst = Bp + blk * 2 * (NT * KC);
+  const int k8 = e % 8, n8 = (e / 8) % 8, kg = (e / 64) % (KC / 8), ng = e / (64 * (KC / 8));
+  const int n = tn * NT + ng * 8 + n8, k = kc * KC + kg * 8 + k8;
+  const float x = (n < N && k < K) ? W[((long long)t * K + k) * N + n] : 0.f;
+  const __half h = __float2half_rn(x);
+  __half* dst = Bp + blk * 2 * (NT * KC);
   dst[e] = h;
-  dst[NT * KC + e] = x - h;
+  dst[NT * KC + e] = __float2half_rn(x - __half2float(h));
 }
 
 }  // namespace gt
 
-CDSEG_API size_t cdseg_gemm_packed_b_floats(int T, int K, int N) {
-  return (size_t)T * (K / gt::KC) * ((N + gt::NT - 1) / gt::NT) * 2 * gt::NT * gt::KC;
+CDSEG_API size_t cdseg_gemm_packed_b_floats(int T, int K, int N) {   // size in 4-byte units (the blocks hold fp16 pairs)
+  return (size_t)T * ((K + gt::KC - 1) / gt::KC) * ((N + gt::NT - 1) / gt::NT) * gt::NT * gt::KC;
 }
 
-// W: fp32 [T][K][N] -> Bp (cdseg_gemm_packed_b_floats floats).  K % 16 == 0.
+// W: fp32 [T][K][N] -> Bp (cdseg_gemm_packed_b_floats 4-byte units).  K % 16 == 0.
 CDSEG_API int cdseg_gemm_pack_b(const float* W, int T, int K, int N, float* Bp, void* stream) {
-  if (T <= 0 || K <= 0 || (K % gt::KC) || N <= 0) return CDSEG_EINVAL;
-  const long long total = (long long)T * (K / gt::KC) * ((N + gt::NT - 1) / gt::NT) * gt::NT * gt::KC;
-  gt::pack_b_kernel<<<cdseg_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(W, T, K, N, Bp);
+  if (T <= 0 || K <= 0 || (K % 16) || N <= 0) return CDSEG_EINVAL;
+  const long long total = (long long)T * ((K + gt::KC - 1) / gt::KC) * ((N + gt::NT - 1) / gt::NT) * gt::NT * gt::KC;
+  gt::pack_b_kernel<<<cdseg_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(W, T, K, N, reinterpret_cast<__half*>(Bp));
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;
@@ -445,14 +441,14 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
                             int act, float* out, int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes,
                             void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (M < 0 || N <= 0 || K <= 0 || (K % gt::KC) || (lda & 3) || T <= 0 ||
+  if (M < 0 || N <= 0 || K <= 0 || (K % 16) || (lda & 3) || T <= 0 ||
       nsplit < 1 || nsplit > T || (tile_mask && T > 32))
     return CDSEG_EINVAL;
   if (M == 0) return CDSEG_OK;
   if (workspace_bytes < cdseg_gemm_tc_workspace_bytes(M, N, nsplit)) return CDSEG_ENOSPC;
   const int un_max = N >= gt::NT ? gt::NT : ((N + 15) & ~15);
-  const int b_bytes = un_max * gt::KC * 4;
-  const int iters = (int)((long long)T * (K / gt::KC) / nsplit);      // upper bound of k-iterations per CTA
+  const int b_bytes = un_max * gt::KC * 2;
+  const int iters = (int)((long long)T * ((K + gt::KC - 1) / gt::KC) / nsplit);      // upper bound of k-iterations per CTA
   // TMEM: accumulator columns + A ring (32 columns per slot); allocation must be a power of two >= 32
   const int acc_cols = un_max <= 32 ? 32 : (un_max <= 64 ? 64 : 128);
   const int AT = acc_cols == 128 ? 4 : ((iters >= 4 && acc_cols <= 32) ? 3 : 2);   // 32+96=128, 64+64=128, 128+128=256 columns
