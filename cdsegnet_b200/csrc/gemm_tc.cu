@@ -14,12 +14,12 @@
 // these skinny (N = 32..128) GEMMs.  Valid for |x| < 65504 (activations / weights of this network are O(1..100)).
 //
 // CTA = 128 output rows x one N tile (<= 128 columns), 192 threads:
-//   warps 0-3  A producers: coalesced gather (8 lanes per 128-byte row chunk), fp16 hi/lo split, store into shared
-//              memory in the UMMA K-major core-matrix layout; afterwards the epilogue
+//   warps 0-3  A producers (thread == row == TMEM lane): gather 64 B of the row per k-chunk, split hi/lo, store
+//              both into tensor memory (the A operand never touches shared memory); afterwards the epilogue
 //              (TMEM lane == row): + bias, GELU, + residual, fp32 rows to HBM
 //   warp 4     B loader: one TMA bulk copy per k-chunk of the pre-split, pre-tiled weight block
 //   warp 5     MMA issuer: 6 x tcgen05.mma (M128 x N x K8) per k-chunk, commit -> frees the stage
-// 3-stage mbarrier ring (A written by the producer warps, B by TMA); taps that no row of the tile has are skipped via a per-tile tap mask;
+// A ring in TENSOR MEMORY (tcgen05.st by the producers, TS-form MMA), TMA ring for B in shared memory; taps that no row of the tile has are skipped via a per-tile tap mask;
 // optional split over taps (grid.z) for levels with few rows (partials reduced by a second kernel).
 #include "common.cuh"
 
@@ -101,25 +101,16 @@ struct Params {
   float* out; long long ldo;
   float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
   int vec_ok;                             // output / residual rows are 16-byte aligned
-  int S, b_bytes, tmem_cols;              // ring stages, bytes of one B block (hi or lo), TMEM columns (pow2 >= 32)
+  int AT, SB, b_bytes, acc_cols, tmem_cols;   // A ring slots (TMEM), B ring stages (smem), bytes of one B block, TMEM layout
 };
 
 constexpr int MAX_RING = 4;
 constexpr int STG_BYTES = 4 * 32 * 36 * 4;   // epilogue staging: 4 warps x 32 rows x 36 floats
 
-constexpr int A_BYTES = BM * KC * 2;        // one fp16 A tile (hi or lo): 128 rows x 32 k
 struct Bars {
-  uint64_t full_a[MAX_RING], full_b[MAX_RING], empty[MAX_RING], acc;
+  uint64_t full_a[MAX_RING], empty_a[MAX_RING], full_b[MAX_RING], empty_b[MAX_RING], acc;
   uint32_t tmem_slot, pad;
 };
-
-// D[tmem] (+)= A[smem] . B[smem]
-__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
 // D[tmem] (+)= A[tmem] . B[smem]   (A: lane = row, two fp16 K elements per 32-bit column)
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -137,16 +128,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// Gathers are COALESCED: 8 lanes fetch the 8 x 16-byte pieces of one 128-byte row chunk, so a warp-level load touches
-// 4 cache lines instead of 32 (with one row per lane the kernel was bound by L1TEX wavefronts: 32 per instruction,
-// measured 127-162 us for the stage-0 conv whatever the prefetch depth -- profiles/r01_gemm_tc_history.md).  Each lane
-// converts its piece to fp16 hi / lo and stores both into the UMMA K-major core-matrix layout in shared memory.
+// The A operand never touches shared memory: each producer thread gathers its row (prefetched in registers), splits it
+// into fp16 hi / lo and stores both straight into TENSOR MEMORY (lane == row), from where tcgen05.mma reads it (TS form).
+// Variants measured on B200 for the stage-0 conv (120k x 27 taps x 32->32), see profiles/r01_gemm_tc_history.md:
+// smem-A tf32 143 us, +deep cp.async ring 270 us, TMEM-A tf32 152 us, TMEM-A fp16 (this) 127 us, coalesced smem-A 230 us.
 __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int S = p.S, B_BYTES = p.b_bytes;
-  const int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;               // A_hi | A_lo | B_hi | B_lo
-  uint8_t* s_stg = smem;                                            // epilogue staging aliases the (idle) ring
-  Bars* bars = reinterpret_cast<Bars*>(smem + (size_t)S * STAGE_BYTES);
+  const int AT = p.AT, SB = p.SB, B_BYTES = p.b_bytes;
+  uint8_t* s_stg = smem;
+  uint8_t* s_b = smem + STG_BYTES;
+  Bars* bars = reinterpret_cast<Bars*>(s_b + (size_t)SB * 2 * B_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x, tile_n = blockIdx.y, z = blockIdx.z;
   const int ntiles = (p.N + NT - 1) / NT;
@@ -160,8 +151,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_RING; ++s) {
       mbar_init(smem_u32(&bars->full_a[s]), 128);
+      mbar_init(smem_u32(&bars->empty_a[s]), 1);
       mbar_init(smem_u32(&bars->full_b[s]), 1);
-      mbar_init(smem_u32(&bars->empty[s]), 1);
+      mbar_init(smem_u32(&bars->empty_b[s]), 1);
     }
     mbar_init(smem_u32(&bars->acc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -176,6 +168,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
+  const uint32_t tmem_a = tmem + (uint32_t)p.acc_cols;          // A ring: slot q at +32q : [hi 16 cols | lo 16 cols]
 
   // present taps of this CTA's split (identical in every role) -> iteration it = (tap taps[it / kch], chunk it % kch)
   uint8_t taps[32];
@@ -192,11 +185,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   if (warp < 4) {
     // ------------------------------- A producers -------------------------------
     const int r = threadIdx.x;
-    const long long m = (long long)tile_m * BM + r;                      // epilogue row of this thread (TMEM lane)
+    const long long m = (long long)tile_m * BM + r;
+    const bool row_ok = m < p.M;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int g = lane >> 3, c = lane & 7;                               // load mapping: row = 32*warp + 4*i + g, piece c
-    // this tile's neighbour indices, staged once in shared memory (one coalesced block read)
-    int32_t* s_idx = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(bars) + sizeof(Bars) + 64);
+    // this tile's neighbour indices, staged once in shared memory (one coalesced block read) so that the per-tap
+    // row address no longer hangs off a dependent global load
+    int32_t* s_idx = reinterpret_cast<int32_t*>(s_b + (size_t)SB * 2 * B_BYTES + sizeof(Bars) + 64);
     const bool idx_smem = p.idx != nullptr && p.T <= 32;
     if (idx_smem) {
       const long long base = (long long)tile_m * BM * p.T, total = (long long)p.M * p.T;
@@ -205,53 +199,49 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
     }
     auto fetch = [&](int it, float4* v) {
       const int t = tap_of(it), kc = it - (it / kch) * kch;
-      const bool k_ok = kc * KC + c * 4 < p.K;                           // K may be 16 mod 32: the tail pieces are zero
+      long long src = -1;
+      if (idx_smem) src = s_idx[r * p.T + t];
+      else if (row_ok) src = p.idx ? (long long)__ldg(p.idx + m * p.T + t) : m;
+      const int kleft = p.K - kc * KC;                                  // valid fp32 elements of this chunk (K may be 16 mod 32)
+      if (src >= 0) {
+        const float4* row = reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) + kc * (KC / 4);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = warp * 32 + i * 4 + g;
-        const long long mm = (long long)tile_m * BM + rr;
-        long long src = -1;
-        if (idx_smem) src = s_idx[rr * p.T + t];
-        else if (mm < p.M) src = p.idx ? (long long)__ldg(p.idx + mm * p.T + t) : mm;
-        v[i] = (src >= 0 && k_ok)
-                   ? __ldg(reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K) + kc * KC) + c)
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < KC / 4; ++j) v[j] = j * 4 < kleft ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < KC / 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    // two gathers alternate in registers: iteration it+2 is requested right after iteration it has been stored
     auto proc = [&](int it, float4* v) {
-      const int s = it % S, u = it / S;
-      uint2 hi[8], lo[8];
+      const int q = it % AT, u = it / AT;
+      uint32_t hi[KC / 2], lo[KC / 2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const __half2 h0 = __floats2half2_rn(v[i].x, v[i].y), h1 = __floats2half2_rn(v[i].z, v[i].w);
+      for (int j = 0; j < KC / 4; ++j) {
+        const __half2 h0 = __floats2half2_rn(v[j].x, v[j].y), h1 = __floats2half2_rn(v[j].z, v[j].w);
         const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-        const __half2 l0 = __floats2half2_rn(v[i].x - f0.x, v[i].y - f0.y), l1 = __floats2half2_rn(v[i].z - f1.x, v[i].w - f1.y);
-        hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-        lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        const __half2 l0 = __floats2half2_rn(v[j].x - f0.x, v[j].y - f0.y), l1 = __floats2half2_rn(v[j].z - f1.x, v[j].w - f1.y);
+        hi[2 * j] = *reinterpret_cast<const uint32_t*>(&h0); hi[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        lo[2 * j] = *reinterpret_cast<const uint32_t*>(&l0); lo[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l1);
       }
-      if (it + 2 < n_iter) fetch(it + 2, v);                             // registers are free again: request the next gather
-      if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
-      uint8_t* a_hi = smem + (size_t)s * STAGE_BYTES;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = warp * 32 + i * 4 + g;
-        // element (row, k) at (row/8)*512 + (k/8)*128 + (row%8)*16 + (k%8)*2 ; this lane owns k = 4c .. 4c+3
-        const uint32_t off = (uint32_t)((rr >> 3) * 512 + (c >> 1) * 128 + (rr & 7) * 16 + (c & 1) * 8);
-        *reinterpret_cast<uint2*>(a_hi + off) = hi[i];
-        *reinterpret_cast<uint2*>(a_hi + A_BYTES + off) = lo[i];
+      if (it + 2 < n_iter) fetch(it + 2, v);
+      if (u > 0) {
+        mbar_wait(smem_u32(&bars->empty_a[q]), (uint32_t)((u - 1) & 1));
+        tc_fence_after();
       }
-      fence_async_smem();
-      mbar_arrive(smem_u32(&bars->full_a[s]));
+      tmem_st16(tmem_a + lane_base + q * 32, hi);
+      tmem_st16(tmem_a + lane_base + q * 32 + 16, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bars->full_a[q]));
     };
-    float4 v0[8], v1[8];
+    float4 v0[KC / 4], v1[KC / 4];
     if (n_iter > 0) fetch(0, v0);
     if (n_iter > 1) fetch(1, v1);
     for (int it = 0; it < n_iter; it += 2) {
       proc(it, v0);
       if (it + 1 < n_iter) proc(it + 1, v1);
     }
-    const bool row_ok = m < p.M;
-    (void)row_ok;
     // --------------------------------- epilogue ---------------------------------
     // TMEM (lane == row) -> registers -> bias/GELU -> shared-memory staging (each warp only touches its own
     // 32 rows, so __syncwarp suffices) -> coalesced 128-byte row segments to HBM (+ residual, read coalesced).
@@ -320,10 +310,10 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       const uint32_t bbytes = (uint32_t)un * KC * 2;            // prefix of the fp16 hi / lo block (n-groups are outermost)
       for (int it = 0; it < n_iter; ++it) {
         const int t = tap_of(it), kc = it - (it / kch) * kch;
-        const int s = it % S, u = it / S;
-        if (u > 0) mbar_wait(smem_u32(&bars->empty[s]), (uint32_t)((u - 1) & 1));
+        const int s = it % SB, u = it / SB;
+        if (u > 0) mbar_wait(smem_u32(&bars->empty_b[s]), (uint32_t)((u - 1) & 1));
         const __half* blk = reinterpret_cast<const __half*>(p.Bp) + ((((long long)t * kch + kc) * ntiles + tile_n) * 2) * (NT * KC);
-        uint8_t* b_hi = smem + (size_t)s * STAGE_BYTES + 2 * A_BYTES;
+        uint8_t* b_hi = s_b + (size_t)s * 2 * B_BYTES;
         mbar_expect_tx(smem_u32(&bars->full_b[s]), 2 * bbytes);
         tma_load_1d(smem_u32(b_hi), blk, bbytes, smem_u32(&bars->full_b[s]));
         tma_load_1d(smem_u32(b_hi + B_BYTES), blk + NT * KC, bbytes, smem_u32(&bars->full_b[s]));
@@ -335,21 +325,21 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       // kind::f16: D fp32 (1<<4), A = B = F16 (format 0), both K-major, N, M=128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(un >> 3) << 17) | ((128u >> 4) << 24);
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it % S;
-        mbar_wait(smem_u32(&bars->full_a[s]), (uint32_t)((it / S) & 1));
-        mbar_wait(smem_u32(&bars->full_b[s]), (uint32_t)((it / S) & 1));
+        const int q = it % AT, s = it % SB;
+        mbar_wait(smem_u32(&bars->full_a[q]), (uint32_t)((it / AT) & 1));
+        mbar_wait(smem_u32(&bars->full_b[s]), (uint32_t)((it / SB) & 1));
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+        const uint32_t a_hi = tmem_a + q * 32, a_lo = a_hi + 16;
+        const uint32_t b_hi = smem_u32(s_b + (size_t)s * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < KC / 16; ++ks) {                   // K = 16 per MMA = 2 core matrices = 256 B of A and of B
-          const uint64_t ah = make_desc(a_hi + ks * 256, 128, 512), al = make_desc(a_lo + ks * 256, 128, 512);
-          const uint64_t bh = make_desc(b_hi + ks * 256, 128, 512), bl = make_desc(b_lo + ks * 256, 128, 512);
-          umma_f16_ss(tmem, al, bh, idesc, (it | ks) != 0);      // small terms first
-          umma_f16_ss(tmem, ah, bl, idesc, 1);
-          umma_f16_ss(tmem, ah, bh, idesc, 1);
+        for (int ks = 0; ks < KC / 16; ++ks) {                   // K = 16 per MMA: 8 TMEM columns of A, 2 core matrices (256 B) of B
+          const uint64_t bh = make_desc(b_hi + ks * 256, 128, (KC / 8) * 128), bl = make_desc(b_lo + ks * 256, 128, (KC / 8) * 128);
+          umma_f16_ts(tmem, a_lo + ks * 8, bh, idesc, (it | ks) != 0);     // small terms first
+          umma_f16_ts(tmem, a_hi + ks * 8, bl, idesc, 1);
+          umma_f16_ts(tmem, a_hi + ks * 8, bh, idesc, 1);
         }
-        umma_commit(smem_u32(&bars->empty[s]));
+        umma_commit(smem_u32(&bars->empty_a[q]));                // each commit tracks every MMA issued so far
+        umma_commit(smem_u32(&bars->empty_b[s]));
       }
       umma_commit(smem_u32(&bars->acc));
     }
@@ -459,11 +449,14 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   const int un_max = N >= gt::NT ? gt::NT : ((N + 15) & ~15);
   const int b_bytes = un_max * gt::KC * 2;
   const int iters = (int)((long long)T * ((K + gt::KC - 1) / gt::KC) / nsplit);      // upper bound of k-iterations per CTA
-  const int tmem_cols = un_max <= 32 ? 32 : (un_max <= 64 ? 64 : 128);
-  const int stage_bytes = 2 * gt::A_BYTES + 2 * b_bytes;
-  int S = iters >= 3 ? 3 : 2;
-  if ((size_t)S * stage_bytes < (size_t)gt::STG_BYTES) S = 3;          // the epilogue staging aliases the ring
-  const size_t smem = (size_t)S * stage_bytes + sizeof(gt::Bars) + 64 + ((idx && T <= 32) ? (size_t)gt::BM * T * 4 : 0) + 1024;
+  // TMEM: accumulator columns + A ring (32 columns per slot); allocation must be a power of two >= 32
+  const int acc_cols = un_max <= 32 ? 32 : (un_max <= 64 ? 64 : 128);
+  const int AT = acc_cols == 128 ? 4 : ((iters >= 4 && acc_cols <= 32) ? 3 : 2);   // 32+96=128, 64+64=128, 128+128=256 columns
+  int tmem_cols = 32;
+  while (tmem_cols < acc_cols + AT * 32) tmem_cols <<= 1;
+  const int SB = iters >= 4 ? (un_max <= 64 ? 4 : 3) : 2;
+  const size_t smem = (size_t)gt::STG_BYTES + (size_t)SB * 2 * b_bytes + sizeof(gt::Bars) + 64 +
+                      ((idx && T <= 32) ? (size_t)gt::BM * T * 4 : 0) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(gt::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -474,7 +467,7 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp;
   p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.ldr = ldr; p.act = act; p.out = out; p.ldo = ldo;
   p.part = (float*)workspace; p.nsplit = nsplit;
-  p.S = S; p.b_bytes = b_bytes; p.tmem_cols = tmem_cols;
+  p.AT = AT; p.SB = SB; p.b_bytes = b_bytes; p.acc_cols = acc_cols; p.tmem_cols = tmem_cols;
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + gt::NT - 1) / gt::NT, nsplit);
