@@ -430,6 +430,7 @@ class PointTransformerV3(nn.Module):
         # evaluate the timestep MLP once per scene when the t_emb rows are uniform inside each scene
         # (always true for DefaultSegmentorV2: default.py:400-402, 451-454); False forces the per-point path
         self.t_emb_per_scene = True
+        self.overlap_streams = True          # run the Noise Network on a second CUDA stream beside the Conditional Network
         self.n_cfg = dict(stride=n_stride, enc_depths=n_enc_depths, dec_depths=n_dec_depths)
         self.c_cfg = dict(stride=c_stride, enc_depths=c_enc_depths, dec_depths=c_dec_depths)
         no = len(self.order)
@@ -557,20 +558,46 @@ class PointTransformerV3(nn.Module):
                     raise ValueError("t_emb must have one row per point (or one per scene)")
                 t = self.fc_t1(c["t_emb"]); t = t * torch.sigmoid(t)      # c["t_emb"] is already in internal numbering
                 t = self.fc_t2(t); c["t_emb"] = t * torch.sigmoid(t)
-        c = self._c_embedding(c)
-        c = self._run_stage(self._c_enc[0], c, cl, 0, exact); n = self._run_stage(self._n_enc[0], n, nl, 0, exact)
-        c = self._run_stage(self._c_enc[1], c, cl, 1, exact); n = self._run_stage(self._n_enc[1], n, nl, 1, exact)
-        n = self._run_stage(self._n_enc[2], n, nl, 2, exact)
-        c = self._run_stage(self._c_enc[2], c, cl, 2, exact); n = self._run_stage(self._n_enc[3], n, nl, 3, exact)
-        n = self._run_stage(self._n_enc[4], n, nl, 4, exact)
+        # The two networks only meet in the TransferModule (ptv3.py:1785-1808): the Noise Network runs on a second
+        # CUDA stream next to the Conditional Network so that the latency-bound coarse levels of one fill the SMs
+        # the other leaves idle.  Events order the hand-offs; tensors that cross streams are record_stream()'ed.
+        main = torch.cuda.current_stream()
+        side = self._side_stream(main) if self.overlap_streams else main
+        two = side is not main
+        if two:
+            nl[0].nbr(5); nl[0].nbr(3); nl[0].tile_mask(3)          # level-0 tables are shared by both branches: build first
+            for k in ("feat", "coord", "t_scene", "t_emb"):
+                if k in c and torch.is_tensor(c[k]):
+                    c[k].record_stream(side)
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            c = self._c_embedding(c)
+            for s_ in range(3):
+                c = self._run_stage(self._c_enc[s_], c, cl, s_, exact)
+        for s_ in range(5):
+            n = self._run_stage(self._n_enc[s_], n, nl, s_, exact)
+        if two:
+            main.wait_stream(side)
         c, n = self._tm_dec0(c, n, exact)
-        c = self._run_stage(self._c_dec[0], c, cl, None, exact)
-        n = self._run_stage(self._n_dec[0], n, nl, None, exact); n = self._run_stage(self._n_dec[1], n, nl, None, exact)
-        c = self._run_stage(self._c_dec[1], c, cl, None, exact)
-        n = self._run_stage(self._n_dec[2], n, nl, None, exact); n = self._run_stage(self._n_dec[3], n, nl, None, exact)
-        c["feat"] = linear(c["feat"], self._c_head.weight, self._c_head.bias)
+        if two:
+            c["feat"].record_stream(side)                            # LN(kv) was produced on the main stream
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            c = self._run_stage(self._c_dec[0], c, cl, None, exact)
+            c = self._run_stage(self._c_dec[1], c, cl, None, exact)
+            c["feat"] = linear(c["feat"], self._c_head.weight, self._c_head.bias)
+        for j in range(4):
+            n = self._run_stage(self._n_dec[j], n, nl, None, exact)
         n["feat"] = linear(n["feat"], self._n_head.weight, self._n_head.bias)
+        if two:
+            main.wait_stream(side)
         return self._export(c), self._export(n)
+
+    def _side_stream(self, main):
+        key = main.device
+        if getattr(self, "_side", None) is None or self._side[0] != key:
+            self._side = (key, torch.cuda.Stream(device=main.device))
+        return self._side[1]
 
     @staticmethod
     def _export(p):

@@ -117,3 +117,24 @@ def test_simt_gemm_mode_still_matches():
     finally:
         ops.GEMM_MODE = "tc"
     assert np.abs(n["feat"].cpu().numpy() - z["n_feat"]).max() < 1e-3
+
+
+def test_single_stream_mode_matches():
+    """overlap_streams=False (everything on the caller's stream) gives the same logits as the two-stream schedule"""
+    z, cfg, shapes = load_case("case1_single")
+    import cdsegnet_b200 as cb
+    from cdsegnet_b200.segmentor import calc_t_emb
+    outs = []
+    for overlap in (True, False):
+        m = cb.PointTransformerV3(**dict(cfg, enable_flash=False))
+        m.load_state_dict(synth_state_dict(shapes), strict=True)
+        m = m.to(DEV).eval()
+        m.overlap_streams = overlap
+        base = dict(coord=t(z["coord"]).to(DEV), grid_coord=t(z["grid_coord"]).to(DEV), offset=t(z["offset"]).to(DEV))
+        ts = 999 * torch.ones((len(z["coord"]), 1), dtype=torch.int64, device=DEV)
+        for _ in range(3):      # repeat: cross-stream lifetime bugs show up on re-use of cached allocator blocks
+            c, n = m(dict(base, feat=t(z["noise"]).to(DEV), t_emb=calc_t_emb(ts, 128)), dict(base, feat=t(z["feat"]).to(DEV)),
+                     perm_fn=replay(z["perms"]))
+            torch.cuda.synchronize()
+            assert np.abs(n["feat"].cpu().numpy() - z["n_feat"]).max() < 1e-3
+            assert np.abs(c["feat"].cpu().numpy() - z["c_feat"]).max() < 1e-3
