@@ -225,18 +225,38 @@ def run_cuda(args):
     e2e = world * n * args.steps / (ms_e2e / 1e3)
     hbm, tf_burst, tf_sust, which = peaks()
 
-    # dominant kernel: the tcgen05 patch-attention launches of the largest stage (CN/NN stage 0, C=32)
-    roof = None
+    # Per-kernel numbers, measured live with CUDA events on the launching stream inside the timed steps above.
+    #  * dominant kernel by device time = gt::gemm_tc_kernel (profiles/): a skinny, HBM-bound GEMM.  Representative launch:
+    #    the stage-0 MLP fc1 (120k x 32 -> 128, bias + GELU fused).  Algorithmic bytes = read A (n*C*4) + write out
+    #    (n*4C*4) + packed weights (read once).
+    #  * the one dense contraction north_star names = tc::attn_tc_kernel at stage 0 (tensor/MUFU bound).
+    roof = attn = None
     if prof:
-        big = max(p[2] for p in prof)
-        sel = [p for p in prof if p[2] == big]
-        dur = sum(a.elapsed_time(b) for a, b, _, _ in sel) / len(sel)
-        ach = big / (dur * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "tc::attn_tc_kernel (stage 0: %d launches/step)" % (len(sel) // args.steps),
-                "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s", "frac": ach / tf_sust, "traffic": None,
-                "peak_source": which + " bf16_tflops_sustained (kernel timed inside the step)",
-                "flops_per_launch": big, "ms_per_launch": dur, "exp_per_launch": sel[0][3],
-                "gexp_per_s": sel[0][3] / (dur * 1e-3) / 1e9}
+        lib = ops._lib.load()
+        import ctypes
+
+        def ms(e0, e1):
+            v = ctypes.c_float(0)
+            lib.cdseg_event_elapsed_ms(e0, e1, ctypes.byref(v))
+            return v.value
+        nmax = max(p["n"] for p in prof)
+        sel = [p for p in prof if p["n"] == nmax and p["C"] == 32]
+        t_attn = sum(ms(p["ev"][0], p["ev"][1]) for p in sel) / len(sel)
+        t_fc1 = sum(ms(p["ev"][2], p["ev"][3]) for p in sel) / len(sel)
+        p0 = sel[0]
+        fl = 4.0 * p0["pairs"] * p0["C"]
+        ex = p0["pairs"] * p0["H"]
+        attn = {"bound": "tensor", "kernel": "tc::attn_tc_kernel (stage 0, %d launches/step)" % (len(sel) // args.steps),
+                "achieved": fl / (t_attn * 1e-3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s", "frac": fl / (t_attn * 1e-3) / 1e12 / tf_sust,
+                "flops_per_launch": fl, "ms_per_launch": t_attn, "exp_per_launch": ex, "gexp_per_s": ex / (t_attn * 1e-3) / 1e9,
+                "mufu_peak_gexp_per_s": 148 * 16 * 1.965, "traffic": None}
+        by = p0["n"] * p0["C"] * 4 + p0["n"] * 4 * p0["C"] * 4 + 2 * 4 * p0["C"] * p0["C"] * 2
+        roof = {"bound": "hbm", "kernel": "gt::gemm_tc_kernel (stage-0 MLP fc1 120000x32->128 + GELU, %d launches/step)" % (len(sel) // args.steps),
+                "achieved": by / (t_fc1 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / (t_fc1 * 1e-3) / 1e9 / hbm,
+                "peak_source": which, "bytes_per_launch": by, "ms_per_launch": t_fc1, "traffic": None}
+        for p in prof:
+            for e in p["ev"]:
+                lib.cdseg_event_destroy(e)
 
     line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -250,7 +270,7 @@ def run_cuda(args):
             "e2e": {"value": e2e, "unit": "points/s",
                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) + n * 6 * 4),
                     "d2h_bytes_per_step": int(n * 20 * 4), "ms_per_step": ms_e2e / args.steps},
-            "roofline": roof}
+            "roofline": roof, "roofline_attention": attn}
     if rank == 0:
         if world == 1 and not args.no_cpu:
             v, cores, dt = cpu_forward_timed(args.cpu_points)

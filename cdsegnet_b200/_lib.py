@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
-SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "gemm_tc.cu"]
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "gemm_tc.cu", "block_exec.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
@@ -64,6 +64,17 @@ _L = ctypes.c_int64
 _F = ctypes.c_float
 _Z = ctypes.c_size_t
 
+class BlockArgs(ctypes.Structure):
+    """mirror of CdsegBlockArgs (include/cdseg_b200.h)"""
+    _fields_ = [("n", ctypes.c_int64), ("C", _I), ("H", _I), ("T_dim", _I), ("B", _I),
+                ("x", _P), ("conv_in", _P), ("nbr", _P), ("tile_mask", _P), ("batch", _P), ("t_scene", _P),
+                ("slot_src", _P), ("slot_dst", _P), ("patch_len", _P), ("T", _I), ("Kp", _I), ("scale", _F),
+                ("conv_Bp", _P), ("conv_b", _P), ("lin_Bp", _P), ("lin_b", _P), ("cpe_g", _P), ("cpe_b", _P),
+                ("t_W", _P), ("t_b", _P), ("n1_g", _P), ("n1_b", _P), ("qkv_Bp", _P), ("qkv_b", _P), ("proj_Bp", _P),
+                ("proj_b", _P), ("n2_g", _P), ("n2_b", _P), ("fc1_Bp", _P), ("fc1_b", _P), ("fc2_Bp", _P), ("fc2_b", _P),
+                ("ln_eps", _F), ("out", _P), ("scratch", _P), ("scratch_bytes", _Z), ("ev", _P * 4)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/cdseg_b200.h
 SIGNATURES = {
     "cdseg_abi_version": (_I, []),
@@ -98,6 +109,11 @@ SIGNATURES = {
     "cdseg_gemm_pack_b": (_I, [_P, _I, _I, _I, _P, _P]),
     "cdseg_tile_tap_mask": (_I, [_P, _L, _I, _P, _P]),
     "cdseg_gemm_tc_workspace_bytes": (_Z, [_L, _I, _I]),
+    "cdseg_block_scratch_bytes": (_Z, [_L, _I, _I, _I, _I, _I]),
+    "cdseg_block_forward": (_I, [ctypes.POINTER(BlockArgs), _P]),
+    "cdseg_event_create": (_P, []),
+    "cdseg_event_destroy": (None, [_P]),
+    "cdseg_event_elapsed_ms": (_I, [_P, _P, ctypes.POINTER(_F)]),
     "cdseg_gemm_tc": (_I, [_P, _L, _P, _I, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P, _L, _I, _P, _Z, _P]),
 }
 

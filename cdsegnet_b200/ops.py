@@ -12,23 +12,52 @@ from . import _lib
 from ._lib import check
 
 ORDER_IDS = {"z": 0, "z-trans": 1, "hilbert": 2, "hilbert-trans": 3}
-PROFILE = None     # bench.py sets this to a list to collect (start_event, end_event, flops, exps) per attention launch
+PROFILE = None     # bench.py sets this to a list: per Block a dict(ev=[4 raw cudaEvent_t], n, C, H, pairs) (see Block._native)
 
 
 def _p(t, dtype=None):
+    """raw device pointer of a tensor (None -> NULL).  The checks are cheap attribute reads; a CPU tensor, a
+    non-contiguous view or a wrong dtype must raise (there is no CPU fallback and no silent conversion)."""
     if t is None:
         return None
+    if not t.is_cuda or not t.is_contiguous() or (dtype is not None and t.dtype is not dtype):
+        _bad(t, dtype)
+    return t.data_ptr()
+
+
+def _bad(t, dtype):
     if not t.is_cuda:
         raise _lib.CdsegError("cdsegnet_b200 kernels need CUDA tensors (there is no CPU fallback)")
     if not t.is_contiguous():
         raise _lib.CdsegError("tensor must be contiguous")
-    if dtype is not None and t.dtype != dtype:
-        raise _lib.CdsegError(f"expected {dtype}, got {t.dtype}")
-    return ctypes.c_void_p(t.data_ptr())
+    raise _lib.CdsegError(f"expected {dtype}, got {t.dtype}")
+
+
+_STREAM = [None]        # raw cudaStream_t pinned by stream_scope(); torch.cuda.current_stream() costs ~4 us per call
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    s = _STREAM[0]
+    return s if s is not None else torch.cuda.current_stream().cuda_stream
+
+
+class stream_scope:
+    """`with stream_scope(stream):` makes `stream` torch's current stream AND pins its raw handle for the kernel
+    wrappers, so the ~1000 launches of a forward do not each query torch for the current stream."""
+
+    def __init__(self, stream):
+        self.stream = stream
+        self.ctx = torch.cuda.stream(stream)
+
+    def __enter__(self):
+        self.ctx.__enter__()
+        self.prev = _STREAM[0]
+        _STREAM[0] = self.stream.cuda_stream
+        return self
+
+    def __exit__(self, *a):
+        _STREAM[0] = self.prev
+        return self.ctx.__exit__(*a)
 
 
 def _ws(nbytes, device):
@@ -183,14 +212,8 @@ def attn(q, k, v, pm, H, scale, n_out, exact=False):
     C = H * 16
     out = torch.empty((n_out, C), dtype=torch.float32, device=q.device)
     fn = lib.cdseg_attn_exact if exact else lib.cdseg_attn_tc
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
     check(fn(_p(q), _p(k), _p(v), _p(pm["patch_len"]), _p(pm["slot_dst"]), H, pm["T"], pm["Kp"], float(scale), _p(out),
              C, _stream()), "attn")
-    if PROFILE is not None:
-        e1.record()
-        PROFILE.append((e0, e1, 4.0 * pm["pairs"] * C, pm["pairs"] * H))
     return out
 
 
@@ -252,7 +275,20 @@ def tile_tap_mask(nbr):
     return mask
 
 
-GEMM_MODE = "tc"      # "tc": tcgen05 3xTF32 kernels for conv + linears ; "simt": round-1a SIMT conv + cuBLAS SGEMM
+GEMM_MODE = "tc"      # "tc": tcgen05 split-fp16 kernels for conv + linears ; "simt": round-1a SIMT conv + cuBLAS SGEMM
+NATIVE_BLOCKS = True  # run each PTv3 Block through the C++ executor (cdseg_block_forward) instead of launch-by-launch
+
+_ARENAS = {}
+
+
+def arena(nbytes, device):
+    """grow-only scratch arena per (device, CUDA stream): blocks on one stream run back to back, so they can share it"""
+    key = (device.index, _stream())
+    a = _ARENAS.get(key)
+    if a is None or a.numel() < nbytes:
+        a = torch.empty(int(nbytes * 1.25), dtype=torch.uint8, device=device)
+        _ARENAS[key] = a
+    return a
 
 
 def pick_split(tiles, T):

@@ -120,6 +120,14 @@ class _PackCache:
 _PACK = _PackCache()
 
 
+def packed_linear(w, b=None):
+    """(packed tensor-core operand blocks, fp32 bias) of a plain Linear, cached (shared with linear())"""
+    def build():
+        bf = b.detach().float().contiguous() if b is not None else None
+        return ops.gemm_pack_b(w.detach().float().t().contiguous()[None]), bf
+    return _PACK.get((id(w), None), [w, b], build)
+
+
 def linear(x, w, b=None, act=0, res=None, bn=None, cols=None):
     """act(bn(x @ w[:, cols]^T + b)) + res.  tcgen05 3xTF32 GEMM with everything fused in the epilogue
     (eval-mode BatchNorm is folded into the packed weight/bias); cuBLAS SGEMM path for ops.GEMM_MODE == "simt"."""
@@ -216,8 +224,54 @@ class Block(nn.Module):
         if T_dim != -1:
             self.t_mlp = nn.Linear(T_dim, channels)
 
+    def _native(self, point, level):
+        """the whole block through ONE C-ABI call (cdseg_block_forward): same kernels, enqueued from C++"""
+        import ctypes
+        from ._lib import BlockArgs, load, check
+        x = point["feat"]
+        n, C = x.shape
+        conv_in = point.pop("conv_in", None)
+        pm = level.patch_maps(self.attn.order_index, self.attn.patch_size)
+        a = BlockArgs()
+        a.n, a.C, a.H, a.T_dim, a.B = n, C, self.attn.num_heads, max(self.T_dim, 0), level.B
+        a.x = x.data_ptr(); a.conv_in = conv_in.data_ptr() if conv_in is not None else None
+        a.nbr = level.nbr(3).data_ptr(); a.tile_mask = level.tile_mask(3).data_ptr(); a.batch = level.batch.data_ptr()
+        ts = point.get("t_scene") if self.T_dim != -1 else None
+        a.t_scene = ts.data_ptr() if ts is not None else None
+        a.slot_src, a.slot_dst, a.patch_len = pm["slot_src"].data_ptr(), pm["slot_dst"].data_ptr(), pm["patch_len"].data_ptr()
+        a.T, a.Kp, a.scale = pm["T"], pm["Kp"], float(self.attn.scale)
+        conv = self.cpe[0]
+        a.conv_Bp = _PACK.get((id(conv.weight), "conv"), [conv.weight], lambda: ops.gemm_pack_b(conv.wt())).data_ptr()
+        a.conv_b = conv.bias.data_ptr()
+        for name, lin in (("lin", self.cpe[1]), ("qkv", self.attn.qkv), ("proj", self.attn.proj), ("fc1", self.mlp[0].fc1),
+                          ("fc2", self.mlp[0].fc2)):
+            Bp, bias = packed_linear(lin.weight, lin.bias)
+            setattr(a, name + "_Bp", Bp.data_ptr()); setattr(a, name + "_b", bias.data_ptr())
+        a.cpe_g, a.cpe_b = self.cpe[2].weight.data_ptr(), self.cpe[2].bias.data_ptr()
+        if ts is not None:
+            a.t_W, a.t_b = self.t_mlp.weight.data_ptr(), self.t_mlp.bias.data_ptr()
+        a.n1_g, a.n1_b = self.norm1[0].weight.data_ptr(), self.norm1[0].bias.data_ptr()
+        a.n2_g, a.n2_b = self.norm2[0].weight.data_ptr(), self.norm2[0].bias.data_ptr()
+        a.ln_eps = self.norm1[0].eps
+        lib = load()
+        need = lib.cdseg_block_scratch_bytes(n, C, a.H, a.T, a.Kp, a.B)
+        arena = ops.arena(need, x.device)
+        out = torch.empty_like(x)
+        a.out, a.scratch, a.scratch_bytes = out.data_ptr(), arena.data_ptr(), arena.numel()
+        if ops.PROFILE is not None:      # bench.py: time the attention kernel and the fc1 GEMM of this block with CUDA events
+            ev = [lib.cdseg_event_create() for _ in range(4)]
+            for i in range(4):
+                a.ev[i] = ev[i]
+            ops.PROFILE.append(dict(ev=ev, n=n, C=C, H=a.H, pairs=pm["pairs"]))
+        check(lib.cdseg_block_forward(ctypes.byref(a), ops._stream()), "block_forward")
+        point["feat"] = out
+        return point
+
     def forward(self, point, exact):
         level = point["_level"]
+        if (ops.GEMM_MODE == "tc" and ops.NATIVE_BLOCKS and not exact
+                and (self.T_dim == -1 or "t_scene" in point or "t_emb" not in point)):
+            return self._native(point, level)
         x = point["feat"]
         conv_in = point.pop("conv_in", x)             # stale sparse_conv_feat quirk, see SerializedUnpooling
         y = self.cpe[0](conv_in, level)
@@ -513,6 +567,13 @@ class PointTransformerV3(nn.Module):
     def forward(self, c_point=None, n_point=None, perm_fn=None):
         if self.training:
             raise NotImplementedError("cdsegnet_b200 round 1 implements the inference forward only")
+        dev = (n_point if n_point is not None else c_point)["coord"].device
+        if dev.type != "cuda":
+            raise RuntimeError("cdsegnet_b200: inputs must be CUDA tensors (no CPU fallback)")
+        with ops.stream_scope(torch.cuda.current_stream(dev)):
+            return self._forward(c_point, n_point, perm_fn)
+
+    def _forward(self, c_point, n_point, perm_fn):
         exact = self.exact_attention
         src = n_point
         flags = None
@@ -570,7 +631,7 @@ class PointTransformerV3(nn.Module):
                 if k in c and torch.is_tensor(c[k]):
                     c[k].record_stream(side)
             side.wait_stream(main)
-        with torch.cuda.stream(side):
+        with ops.stream_scope(side):
             c = self._c_embedding(c)
             for s_ in range(3):
                 c = self._run_stage(self._c_enc[s_], c, cl, s_, exact)
@@ -582,7 +643,7 @@ class PointTransformerV3(nn.Module):
         if two:
             c["feat"].record_stream(side)                            # LN(kv) was produced on the main stream
             side.wait_stream(main)
-        with torch.cuda.stream(side):
+        with ops.stream_scope(side):
             c = self._run_stage(self._c_dec[0], c, cl, None, exact)
             c = self._run_stage(self._c_dec[1], c, cl, None, exact)
             c["feat"] = linear(c["feat"], self._c_head.weight, self._c_head.bias)

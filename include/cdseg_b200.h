@@ -128,6 +128,29 @@ int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int T, const 
                   int64_t M, int N, int K, const float* bias, const float* res, int64_t ldr, int act, float* out,
                   int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- native executor of one PTv3 Block (ptv3.py:399-428): the 12-13 launches above enqueued from C++ in one call --- */
+typedef struct CdsegBlockArgs {
+  int64_t n; int C, H, T_dim, B;                 /* points, channels, heads (C = 16 H), timestep width, scenes */
+  const float* x; const float* conv_in;           /* block input; conv_in != NULL: tensor the CPE conv reads (stale-feature quirk) */
+  const int32_t* nbr; const uint32_t* tile_mask; const int32_t* batch;
+  const float* t_scene;                           /* [B, T_dim] per-scene timestep features or NULL (CN blocks) */
+  const int32_t* slot_src; const int32_t* slot_dst; const int32_t* patch_len; int T, Kp; float scale;
+  const float* conv_Bp; const float* conv_b;      /* packed operands come from cdseg_gemm_pack_b */
+  const float* lin_Bp; const float* lin_b; const float* cpe_g; const float* cpe_b;
+  const float* t_W; const float* t_b;
+  const float* n1_g; const float* n1_b; const float* qkv_Bp; const float* qkv_b; const float* proj_Bp; const float* proj_b;
+  const float* n2_g; const float* n2_b; const float* fc1_Bp; const float* fc1_b; const float* fc2_Bp; const float* fc2_b;
+  float ln_eps;
+  float* out; void* scratch; size_t scratch_bytes; /* out [n,C]; scratch >= cdseg_block_scratch_bytes(...) */
+  void* ev[4];                                    /* optional cudaEvent_t: recorded before/after the attention kernel and before/after fc1 */
+} CdsegBlockArgs;
+size_t cdseg_block_scratch_bytes(int64_t n, int C, int H, int T, int Kp, int B);
+int cdseg_block_forward(const CdsegBlockArgs* args, void* stream);
+/* CUDA events for live per-kernel timing inside the timed region (bench.py) */
+void* cdseg_event_create(void);
+void cdseg_event_destroy(void* e);
+int cdseg_event_elapsed_ms(void* e0, void* e1, float* ms);
+
 #ifdef __cplusplus
 }
 #endif
