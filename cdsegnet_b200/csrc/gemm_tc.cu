@@ -26,7 +26,7 @@
 namespace gt {
 
 constexpr int BM = 128;
-constexpr int NT = 128;                // max N tile (TMEM columns)
+constexpr int NT = 128;                // max N tile (TMEM columns); NT = 64 (4 CTAs per SM) measured no faster: 19.36 vs 19.08 ms/step
 constexpr int KC = 32;                 // fp32 elements per k-chunk (128 B per row) = 2 MMA K-steps of 16
 constexpr int NTHREADS = 192;
 // a stage holds A_hi | A_lo | B_hi | B_lo ; the B blocks are sized for this launch's widest N tile
