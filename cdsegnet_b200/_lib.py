@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
-SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "gemm_tc.cu", "block_exec.cu"]
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "block_exec.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
@@ -98,6 +98,8 @@ SIGNATURES = {
     "cdseg_subm_conv": (_I, [_P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _I, _P, _P]),
     "cdseg_attn_pack_f16": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "cdseg_attn_pack_f32": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "cdseg_attn_pack_f16v": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "cdseg_attn_tc2": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
     "cdseg_attn_tc_smem_bytes": (_Z, [_I]),
     "cdseg_attn_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
     "cdseg_attn_exact": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),

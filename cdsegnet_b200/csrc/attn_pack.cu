@@ -16,11 +16,17 @@
 // with plain 1-D bulk copies.  Slots with slot_src < 0 are zero rows.
 #include "common.cuh"
 
+CDSEG_API int cdseg_attn_pack_f16v(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src,
+                                   int H, int T, int Kp, void* dst0, void* dst1, void* dst2, int v_ones, void* stream);
+
 // src: fp32 rows [n, ld] ; column block for (which, h) starts at col0 + which*C + h*16
+// v_ones_which >= 0: that tensor (V) is written 32 wide per key: [v(16) | 1 | 0 x 15], i.e. the MN-major B operand of
+// ONE tcgen05.mma that yields P.V and the row sum P.1 together (block layout (k/8)*256 + (n/8)*64 + (k%8)*8 + n%8 elements).
 template <typename OutT>
 __global__ void pack_heads_kernel(const float* __restrict__ src, int64_t ld, int col0, int C, int nwhich,
                                   const int32_t* __restrict__ slot_src, int H, int T, int Kp,
-                                  OutT* __restrict__ dst0, OutT* __restrict__ dst1, OutT* __restrict__ dst2) {
+                                  OutT* __restrict__ dst0, OutT* __restrict__ dst1, OutT* __restrict__ dst2,
+                                  int v_ones_which = -1) {
   // consecutive threads -> consecutive slots (16-byte stores of 8 consecutive rows coalesce)
   const int64_t slots = (int64_t)T * Kp;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -40,6 +46,20 @@ __global__ void pack_heads_kernel(const float* __restrict__ src, int64_t ld, int
     for (int j = 0; j < 16; ++j) v[j] = 0.f;
   }
   OutT* dst = which == 0 ? dst0 : (which == 1 ? dst1 : dst2);
+  if constexpr (sizeof(OutT) == 2) {
+    if (which == v_ones_which) {
+      OutT* blk32 = dst + ((int64_t)h * T + t) * Kp * 32;
+      __half2 hh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      uint4* o = reinterpret_cast<uint4*>(blk32 + (r / 8) * 256 + (r % 8) * 8);
+      o[0] = *reinterpret_cast<uint4*>(&hh[0]);                                  // n 0..7
+      o[8] = *reinterpret_cast<uint4*>(&hh[4]);                                  // n 8..15   (+64 elements)
+      o[16] = make_uint4(s >= 0 ? 0x00003C00u : 0u, 0u, 0u, 0u);                 // n 16 = 1.0 (valid keys), n 17..23 = 0
+      o[24] = make_uint4(0u, 0u, 0u, 0u);                                        // n 24..31 = 0
+      return;
+    }
+  }
   OutT* blk = dst + ((int64_t)h * T + t) * Kp * 16;
   if constexpr (sizeof(OutT) == 2) {
     __half2 hh[8];
@@ -59,11 +79,17 @@ __global__ void pack_heads_kernel(const float* __restrict__ src, int64_t ld, int
 // column blocks col0 + w*C.  dst pointers beyond nwhich are ignored.
 CDSEG_API int cdseg_attn_pack_f16(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src,
                                   int H, int T, int Kp, void* dst0, void* dst1, void* dst2, void* stream) {
+  return cdseg_attn_pack_f16v(src, ld, col0, C, nwhich, slot_src, H, T, Kp, dst0, dst1, dst2, 0, stream);
+}
+
+// v_ones != 0: the LAST packed tensor (V) is written 32 wide per key with a ones column (operand of cdseg_attn_tc2)
+CDSEG_API int cdseg_attn_pack_f16v(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src,
+                                   int H, int T, int Kp, void* dst0, void* dst1, void* dst2, int v_ones, void* stream) {
   if (H <= 0 || C != H * 16 || nwhich < 1 || nwhich > 3 || (Kp % 128) || (ld & 3) || (col0 & 3)) return CDSEG_EINVAL;
   const int64_t total = (int64_t)T * Kp * H * nwhich;
   if (total == 0) return CDSEG_OK;
   pack_heads_kernel<__half><<<cdseg_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      src, ld, col0, C, nwhich, slot_src, H, T, Kp, (__half*)dst0, (__half*)dst1, (__half*)dst2);
+      src, ld, col0, C, nwhich, slot_src, H, T, Kp, (__half*)dst0, (__half*)dst1, (__half*)dst2, v_ones ? nwhich - 1 : -1);
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;

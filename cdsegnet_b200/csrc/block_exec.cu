@@ -36,7 +36,7 @@ CDSEG_API size_t cdseg_block_scratch_bytes(int64_t n, int C, int H, int T, int K
   s += 6 * row;                                   // y1, y2, x1, h, o, a  (a doubles as x2-input)
   s += align_up((size_t)n * 3 * C * 4);           // qkv
   s += align_up((size_t)n * 4 * C * 4);           // hidden
-  s += 3 * align_up((size_t)H * T * Kp * 16 * 2); // packed q, k, v (fp16)
+  s += 4 * align_up((size_t)H * T * Kp * 16 * 2); // packed q, k (16 wide) and v (32 wide: [v | 1 | 0..]) in fp16
   s += align_up((size_t)B * C * 4);               // t projection
   s += (size_t)32 << 20;                          // split-K partials: only launches with < 120 output tiles split, so
                                                   // nsplit * M * N * 4 B stays below ~26 MB (see pick_split)
@@ -59,7 +59,7 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
   float* qkv = (float*)take((size_t)n * 3 * C * 4);
   float* hid = (float*)take((size_t)n * 4 * C * 4);
   const size_t pk = (size_t)a->H * a->T * a->Kp * 16 * 2;
-  void* qp = take(pk); void* kp = take(pk); void* vp = take(pk);
+  void* qp = take(pk); void* kp = take(pk); void* vp = take(2 * pk);
   float* tproj = (float*)take((size_t)a->B * C * 4);
   if (p > end) return CDSEG_ENOSPC;
   void* ws = p;
@@ -85,9 +85,9 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
   RUN(cdseg_add_layernorm(a->x, y1, tp, tp ? a->batch : nullptr, a->n1_g, a->n1_b, a->ln_eps, n, C, x1, h, stream));
   // attention
   RUN(run_linear(h, n, C, 3 * C, a->qkv_Bp, a->qkv_b, nullptr, 0, qkv, ws, ws_bytes, stream));
-  RUN(cdseg_attn_pack_f16(qkv, 3 * C, 0, C, 3, a->slot_src, a->H, a->T, a->Kp, qp, kp, vp, stream));
+  RUN(cdseg_attn_pack_f16v(qkv, 3 * C, 0, C, 3, a->slot_src, a->H, a->T, a->Kp, qp, kp, vp, 1, stream));
   if (a->ev[0]) cudaEventRecord((cudaEvent_t)a->ev[0], (cudaStream_t)stream);
-  RUN(cdseg_attn_tc(qp, kp, vp, a->patch_len, a->slot_dst, a->H, a->T, a->Kp, a->scale, o, C, stream));
+  RUN(cdseg_attn_tc2(qp, kp, vp, a->patch_len, a->slot_dst, a->H, a->T, a->Kp, a->scale, o, C, stream));
   if (a->ev[1]) cudaEventRecord((cudaEvent_t)a->ev[1], (cudaStream_t)stream);
   RUN(run_linear(o, n, C, C, a->proj_Bp, a->proj_b, nullptr, 0, att, ws, ws_bytes, stream));
   // residual + norm2 + MLP (fc1+GELU, fc2+residual fused in the GEMM epilogues)

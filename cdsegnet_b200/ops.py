@@ -193,16 +193,24 @@ def subm_conv(x, nbr, wt, bias, ksize, ep_scale=None, ep_shift=None, ep_gelu=Fal
 
 
 # ---------------------------------------------------------------- attention
-def attn_pack(src, col0, C, nwhich, pm, H, exact=False):
-    """Gather rows of src (fp32 [n, ld]) by pm['slot_src'] into per-(head, patch) tiles."""
+ATTN_V2 = True        # tcgen05 attention generation: True = attn_tc2.cu (streamed K/V, merged [V|1] operand), False = attn_tc.cu
+
+
+def attn_pack(src, col0, C, nwhich, pm, H, exact=False, has_v=True):
+    """Gather rows of src (fp32 [n, ld]) by pm['slot_src'] into per-(head, patch) tiles.  With the v2 tensor-core
+    kernel the last tensor (V, when has_v) is packed 32 wide with the ones column."""
     lib = _lib.load()
     T, Kp = pm["T"], pm["Kp"]
     dt = torch.float32 if exact else torch.float16
-    bufs = [torch.empty((H, T, Kp, 16), dtype=dt, device=src.device) for _ in range(nwhich)]
+    v32 = (not exact) and ATTN_V2 and has_v
+    bufs = [torch.empty((H, T, Kp, 32 if (v32 and i == nwhich - 1) else 16), dtype=dt, device=src.device) for i in range(nwhich)]
     ptrs = [_p(b) for b in bufs] + [None] * (3 - nwhich)
-    fn = lib.cdseg_attn_pack_f32 if exact else lib.cdseg_attn_pack_f16
-    check(fn(_p(src, torch.float32), src.shape[1], col0, C, nwhich, _p(pm["slot_src"]), H, T, Kp, *ptrs, _stream()),
-          "attn_pack")
+    if exact:
+        check(lib.cdseg_attn_pack_f32(_p(src, torch.float32), src.shape[1], col0, C, nwhich, _p(pm["slot_src"]), H, T, Kp, *ptrs,
+                                      _stream()), "attn_pack")
+    else:
+        check(lib.cdseg_attn_pack_f16v(_p(src, torch.float32), src.shape[1], col0, C, nwhich, _p(pm["slot_src"]), H, T, Kp, *ptrs,
+                                       int(v32), _stream()), "attn_pack")
     return bufs
 
 
@@ -211,7 +219,7 @@ def attn(q, k, v, pm, H, scale, n_out, exact=False):
     lib = _lib.load()
     C = H * 16
     out = torch.empty((n_out, C), dtype=torch.float32, device=q.device)
-    fn = lib.cdseg_attn_exact if exact else lib.cdseg_attn_tc
+    fn = lib.cdseg_attn_exact if exact else (lib.cdseg_attn_tc2 if v.shape[-1] == 32 else lib.cdseg_attn_tc)
     check(fn(_p(q), _p(k), _p(v), _p(pm["patch_len"]), _p(pm["slot_dst"]), H, pm["T"], pm["Kp"], float(scale), _p(out),
              C, _stream()), "attn")
     return out

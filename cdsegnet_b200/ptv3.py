@@ -394,7 +394,7 @@ class SerializedCrossAttention(nn.Module):
             raise ValueError("TransferModule needs equally sized q / kv levels (ptv3.py:1008-1010)")
         kv_row = kv_level.order[kv_level.rowmap[self.order_index]][: kv_level.n]
         pm_kv = ops.patch_maps(kv_row, q_level.scene_count(), pm["K"])
-        (q,) = ops.attn_pack(linear(xq, self.q.weight, self.q.bias), 0, self.C, 1, pm, self.H, exact)
+        (q,) = ops.attn_pack(linear(xq, self.q.weight, self.q.bias), 0, self.C, 1, pm, self.H, exact, has_v=False)
         k, v = ops.attn_pack(linear(xkv, self.kv.weight, self.kv.bias), 0, self.C, 2, pm_kv, self.H, exact)
         o = ops.attn(q, k, v, pm, self.H, self.scale, xq.shape[0], exact)
         return linear(o, self.proj.weight, self.proj.bias)

@@ -246,6 +246,18 @@ def test_attention_exact_vs_dense_oracle(ops, counts, K, H):
 
 
 @pytest.mark.timeout(120)
+@pytest.mark.parametrize("counts,K,H", [((300,), 128, 2), ((1000, 77, 129), 128, 4), ((2500,), 1024, 2), ((5000,), 1024, 4)])
+def test_attention_tcgen05_v1_kernel_still_correct(ops, counts, K, H):
+    """the first-generation kernel (whole-patch K/V image) stays in the library"""
+    ops.ATTN_V2 = False
+    try:
+        out, ref = _attn_case(ops, counts, K, H, exact=False)
+    finally:
+        ops.ATTN_V2 = True
+    assert (out - ref).abs().max() < 2e-3
+
+
+@pytest.mark.timeout(120)
 @pytest.mark.parametrize("counts,K,H", [((128,), 128, 1), ((300,), 128, 2), ((1000, 77, 129), 128, 4), ((64,), 64, 1),
                                          ((2500,), 1024, 2), ((991,), 1024, 8), ((40, 900), 256, 3), ((5000,), 1024, 4)])
 def test_attention_tcgen05_vs_flash_oracle(ops, counts, K, H):
