@@ -111,6 +111,7 @@ SIGNATURES = {
     "cdseg_gemm_pack_b": (_I, [_P, _I, _I, _I, _P, _P]),
     "cdseg_tile_tap_mask": (_I, [_P, _L, _I, _P, _P]),
     "cdseg_gemm_tc_workspace_bytes": (_Z, [_L, _I, _I]),
+    "cdseg_gemm_tc_set_trace": (None, [_P, _I]),
     "cdseg_block_scratch_bytes": (_Z, [_L, _I, _I, _I, _I, _I]),
     "cdseg_block_forward": (_I, [ctypes.POINTER(BlockArgs), _P]),
     "cdseg_event_create": (_P, []),

@@ -10,6 +10,7 @@
 //   * S, P and O are single-buffered: S is copied to registers at once (so the next QK^T can start), the previous
 //     chunk's O is folded into the register accumulator before P is overwritten -> TMEM 128 columns per CTA.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace tc2 {
 
@@ -98,6 +99,11 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float max3(float a, float b, float c) {   // one FMNMX3 instead of two FMNMX (sm_100+)
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -112,7 +118,8 @@ struct Bars {
   uint32_t tmem_slot, pad;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 3)
+template <int OCC>
+__global__ void __launch_bounds__(NTHREADS, OCC)
 attn_tc2_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, const __half* __restrict__ Vp,
                 const int32_t* __restrict__ patch_len, const int32_t* __restrict__ slot_dst, int H, int T, int Kp, float sl2,
                 float* __restrict__ out, int64_t out_ld) {
@@ -227,16 +234,13 @@ attn_tc2_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
       mbar_arrive(smem_u32(&bars->s_free));                      // S lives in registers now: the next QK^T may start
       const int valid = len - g * NC;                            // keys >= valid are padding
       float mx = -INFINITY;
-      if (valid >= NC) {
+      if (valid < NC) {
 #pragma unroll
-        for (int j = 0; j < NC; ++j) mx = fmaxf(mx, __uint_as_float(s[j]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {
+        for (int j = 0; j < NC; ++j)
           if (j >= valid) s[j] = 0xff800000u;                    // -inf
-          mx = fmaxf(mx, __uint_as_float(s[j]));
-        }
       }
+#pragma unroll
+      for (int j = 0; j < NC; j += 2) mx = max3(mx, __uint_as_float(s[j]), __uint_as_float(s[j + 1]));
       const float m_new = fmaxf(m, mx);
       const float msc = m_new * sl2;
       const float a_g = ex2(m * sl2 - msc);                      // first chunk: m = -inf -> 0
@@ -289,16 +293,23 @@ CDSEG_API int cdseg_attn_tc2(const void* Q, const void* K, const void* V32, cons
   if (H <= 0 || T < 0 || (Kp % 128) || (out_ld & 3)) return CDSEG_EINVAL;
   if (T == 0) return CDSEG_OK;
   const size_t smem = (size_t)tc2::R * tc2::STAGE + tc2::SQ_BYTES + tc2::SP_BYTES + sizeof(tc2::Bars) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc2::attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
+  static int occ = 0;
+  if (!occ) {
+    const char* e = getenv("CDSEG_ATTN_OCC");                    // 3 (113 regs, no spill) or 4 (96 regs, 84 B spill) CTAs per SM
+    occ = (e && e[0] == '4') ? 4 : 3;                            // measured equal (100.4 vs 102.4 us at stage 0): default 3
+    cudaError_t e1 = cudaFuncSetAttribute(tc2::attn_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e2 = cudaFuncSetAttribute(tc2::attn_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e1 != cudaSuccess) return (int)e1;
+    if (e2 != cudaSuccess) return (int)e2;
   }
   dim3 g(Kp / 128, T, H);
   const float sl2 = scale * 1.4426950408889634f;
-  tc2::attn_tc2_kernel<<<g, tc2::NTHREADS, smem, (cudaStream_t)stream>>>((const __half*)Q, (const __half*)K, (const __half*)V32,
-                                                                       patch_len, slot_dst, H, T, Kp, sl2, out, out_ld);
+  if (occ == 3)
+    tc2::attn_tc2_kernel<3><<<g, tc2::NTHREADS, smem, (cudaStream_t)stream>>>((const __half*)Q, (const __half*)K, (const __half*)V32,
+                                                                            patch_len, slot_dst, H, T, Kp, sl2, out, out_ld);
+  else
+    tc2::attn_tc2_kernel<4><<<g, tc2::NTHREADS, smem, (cudaStream_t)stream>>>((const __half*)Q, (const __half*)K, (const __half*)V32,
+                                                                            patch_len, slot_dst, H, T, Kp, sl2, out, out_ld);
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;

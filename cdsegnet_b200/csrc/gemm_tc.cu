@@ -22,6 +22,7 @@
 // A ring in TENSOR MEMORY (tcgen05.st by the producers, TS-form MMA), TMA ring for B in shared memory; taps that no row of the tile has are skipped via a per-tile tap mask;
 // optional split over taps (grid.z) for levels with few rows (partials reduced by a second kernel).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace gt {
 
@@ -102,6 +103,7 @@ struct Params {
   float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
   int vec_ok;                             // output / residual rows are 16-byte aligned
   int AT, SB, b_bytes, acc_cols, tmem_cols;   // A ring slots (TMEM), B ring stages (smem), bytes of one B block, TMEM layout
+  long long* trace; int trace_cta;        // profiling hook: clock64 stamps of one CTA (null in production)
 };
 
 constexpr int MAX_RING = 4;
@@ -110,6 +112,7 @@ constexpr int STG_BYTES = 4 * 32 * 36 * 4;   // epilogue staging: 4 warps x 32 r
 struct Bars {
   uint64_t full_a[MAX_RING], empty_a[MAX_RING], full_b[MAX_RING], empty_b[MAX_RING], acc;
   uint32_t tmem_slot, pad;
+  uint8_t taps[32];                       // present taps of this CTA's split, ascending
 };
 
 // D[tmem] (+)= A[tmem] . B[smem]   (A: lane = row, two fp16 K elements per 32-bit column)
@@ -132,7 +135,8 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // into fp16 hi / lo and stores both straight into TENSOR MEMORY (lane == row), from where tcgen05.mma reads it (TS form).
 // Variants measured on B200 for the stage-0 conv (120k x 27 taps x 32->32), see profiles/r01_gemm_tc_history.md:
 // smem-A tf32 143 us, +deep cp.async ring 270 us, TMEM-A tf32 152 us, TMEM-A fp16 (this) 127 us, coalesced smem-A 230 us.
-__global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
+template <int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int AT = p.AT, SB = p.SB, B_BYTES = p.b_bytes;
   uint8_t* s_stg = smem;
@@ -158,6 +162,16 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
     mbar_init(smem_u32(&bars->acc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  int ntap = t_end - t_begin;
+  if (p.T <= 32) {
+    const uint32_t width = (uint32_t)(t_end - t_begin);
+    const uint32_t present = mask & ((width >= 32 ? 0xffffffffu : ((1u << width) - 1u)) << t_begin);
+    ntap = __popc(present);
+    if (threadIdx.x == 32) {
+      int n = 0;
+      for (uint32_t m = present; m; m &= m - 1) bars->taps[n++] = (uint8_t)(__ffs(m) - 1);
+    }
+  }
   if (warp == 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)),
                  "r"((uint32_t)p.tmem_cols)
@@ -168,19 +182,14 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
+  const bool tr = p.trace && blockIdx.x == p.trace_cta && blockIdx.y == 0 && blockIdx.z == 0;
+  if (tr && threadIdx.x == 0) p.trace[0] = clock64();
   const uint32_t tmem_a = tmem + (uint32_t)p.acc_cols;          // A ring: slot q at +32q : [hi 16 cols | lo 16 cols]
 
-  // present taps of this CTA's split (identical in every role) -> iteration it = (tap taps[it / kch], chunk it % kch)
-  uint8_t taps[32];
-  int ntap = 0;
-  if (p.T <= 32) {
-    for (int t = t_begin; t < t_end; ++t)
-      if ((mask >> t) & 1u) taps[ntap++] = (uint8_t)t;
-  } else {
-    ntap = t_end - t_begin;
-  }
+  // present taps of this CTA's split (listed in shared memory by thread 32 before the barrier above)
+  // -> iteration it = (tap taps[it / kch], chunk it % kch)
   const int n_iter = ntap * kch;
-  auto tap_of = [&](int it) { const int j = it / kch; return p.T <= 32 ? (int)taps[j] : t_begin + j; };
+  auto tap_of = [&](int it) { const int j = it / kch; return p.T <= 32 ? (int)bars->taps[j] : t_begin + j; };
 
   if (warp < 4) {
     // ------------------------------- A producers -------------------------------
@@ -224,6 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
         hi[2 * j] = *reinterpret_cast<const uint32_t*>(&h0); hi[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
         lo[2 * j] = *reinterpret_cast<const uint32_t*>(&l0); lo[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l1);
       }
+      if (tr && threadIdx.x == 0 && it == 0) p.trace[2] = clock64();     // first chunk arrived + converted
       if (it + 2 < n_iter) fetch(it + 2, v);
       if (u > 0) {
         mbar_wait(smem_u32(&bars->empty_a[q]), (uint32_t)((u - 1) & 1));
@@ -234,10 +244,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->full_a[q]));
+      if (tr && threadIdx.x == 0 && it == 0) p.trace[3] = clock64();     // first chunk stored to TMEM + signalled
     };
     float4 v0[KC / 4], v1[KC / 4];
     if (n_iter > 0) fetch(0, v0);
     if (n_iter > 1) fetch(1, v1);
+    if (tr && threadIdx.x == 0) p.trace[1] = clock64();                  // first gathers issued
     for (int it = 0; it < n_iter; it += 2) {
       proc(it, v0);
       if (it + 1 < n_iter) proc(it + 1, v1);
@@ -245,10 +257,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
     // --------------------------------- epilogue ---------------------------------
     // TMEM (lane == row) -> registers -> bias/GELU -> shared-memory staging (each warp only touches its own
     // 32 rows, so __syncwarp suffices) -> coalesced 128-byte row segments to HBM (+ residual, read coalesced).
+    if (tr && threadIdx.x == 0) p.trace[4] = clock64();                  // producer loop done
     if (n_iter > 0) {
       mbar_wait(smem_u32(&bars->acc), 0);
       tc_fence_after();
     }
+    if (tr && threadIdx.x == 0) p.trace[5] = clock64();                  // accumulator complete
     constexpr int SLD = 36;                         // staging row stride in floats (conflict-free float4 access)
     float* stg = reinterpret_cast<float*>(s_stg) + (size_t)warp * 32 * SLD;
     const bool final_out = p.nsplit == 1;
@@ -266,43 +280,60 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
         for (int j = 0; j < 32; ++j) acc[j] = 0u;
       }
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        if (j4 * 4 >= cw) break;
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float x = __uint_as_float(acc[j4 * 4 + j]);
-          const int c = c0 + j4 * 4 + j;
-          if (final_out) {
-            if (p.bias && c < wn) x += __ldg(p.bias + n0 + c);
-            if (p.act == 1) x = gelu_erf(x);
-          }
-          o[j] = x;
-        }
-        *reinterpret_cast<float4*>(stg + lane * SLD + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-      }
+      for (int j4 = 0; j4 < 8; ++j4)
+        if (j4 * 4 < cw)
+          *reinterpret_cast<uint4*>(stg + lane * SLD + j4 * 4) = make_uint4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
       __syncwarp();
+      // write-out: lane owns columns cc..cc+3 of rows rr = 4i + lane/8, so bias is one 4-vector per pass and the
+      // residual reads / output writes are full 128-byte row segments
+      const int cc = (lane & 7) * 4, c = c0 + cc;
+      const bool col_ok = cc < cw && c < wn;
+      const bool vec = p.vec_ok && c + 3 < wn;
+      float b4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (final_out && p.bias && col_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + j < wn) b4[j] = __ldg(p.bias + n0 + c + j);
+      }
+      const bool has_res = final_out && p.res != nullptr;
+      const bool do_gelu = final_out && p.act == 1;
+      const long long m_base = (long long)tile_m * BM + warp * 32 + (lane >> 3);
+      float4 q[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3), cc = (lane & 7) * 4;
-        const long long mm = (long long)tile_m * BM + warp * 32 + rr;
-        const int c = c0 + cc;
-        if (mm < p.M && cc < cw && c < wn) {
-          float4 v = *reinterpret_cast<const float4*>(stg + rr * SLD + cc);
+        const long long mm = m_base + i * 4;
+        q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_res && col_ok && mm < p.M) {
+          const float* rp = p.res + mm * p.ldr + n0 + c;
+          if (vec) q[i] = *reinterpret_cast<const float4*>(rp);
+          else {
+            q[i].x = rp[0];
+            if (c + 1 < wn) q[i].y = rp[1];
+            if (c + 2 < wn) q[i].z = rp[2];
+            if (c + 3 < wn) q[i].w = rp[3];
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long mm = m_base + i * 4;
+        if (mm < p.M && col_ok) {
+          float4 v = *reinterpret_cast<const float4*>(stg + (i * 4 + (lane >> 3)) * SLD + cc);
+          v.x += b4[0]; v.y += b4[1]; v.z += b4[2]; v.w += b4[3];
+          if (do_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+          v.x += q[i].x; v.y += q[i].y; v.z += q[i].z; v.w += q[i].w;
           float* op = obase + mm * old + n0 + c;
-          const float* rp = (final_out && p.res) ? p.res + mm * p.ldr + n0 + c : nullptr;
-          if (c + 3 < wn && p.vec_ok) {
-            if (rp) { const float4 q = *reinterpret_cast<const float4*>(rp); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-            *reinterpret_cast<float4*>(op) = v;
-          } else {
-            if (c + 0 < wn) op[0] = v.x + (rp ? rp[0] : 0.f);
-            if (c + 1 < wn) op[1] = v.y + (rp ? rp[1] : 0.f);
-            if (c + 2 < wn) op[2] = v.z + (rp ? rp[2] : 0.f);
-            if (c + 3 < wn) op[3] = v.w + (rp ? rp[3] : 0.f);
+          if (vec) *reinterpret_cast<float4*>(op) = v;
+          else {
+            op[0] = v.x;
+            if (c + 1 < wn) op[1] = v.y;
+            if (c + 2 < wn) op[2] = v.z;
+            if (c + 3 < wn) op[3] = v.w;
           }
         }
       }
       __syncwarp();
+      if (tr && threadIdx.x == 0 && c0 / 32 < 4) p.trace[6 + c0 / 32] = clock64();   // epilogue pass done
     }
   } else if (warp == 4) {
     // -------------------------------- B loader --------------------------------
@@ -327,7 +358,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
       for (int it = 0; it < n_iter; ++it) {
         const int q = it % AT, s = it % SB;
         mbar_wait(smem_u32(&bars->full_a[q]), (uint32_t)((it / AT) & 1));
+        if (tr && it == 0) p.trace[10] = clock64();                      // MMA: A ready
         mbar_wait(smem_u32(&bars->full_b[s]), (uint32_t)((it / SB) & 1));
+        if (tr && it == 0) p.trace[11] = clock64();                      // MMA: B ready
         tc_fence_after();
         const uint32_t a_hi = tmem_a + q * 32, a_lo = a_hi + 16;
         const uint32_t b_hi = smem_u32(s_b + (size_t)s * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
@@ -342,10 +375,12 @@ __global__ void __launch_bounds__(NTHREADS, 3) gemm_tc_kernel(const Params p) {
         umma_commit(smem_u32(&bars->empty_b[s]));
       }
       umma_commit(smem_u32(&bars->acc));
+      if (tr) p.trace[12] = clock64();                                   // all MMAs issued
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) p.trace[13] = clock64();
   if (warp == 5) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -431,6 +466,11 @@ CDSEG_API int cdseg_tile_tap_mask(const int32_t* nbr, int64_t M, int T, uint32_t
   return CDSEG_OK;
 }
 
+static long long* g_trace = nullptr;
+static int g_trace_cta = 0;
+// profiling hook: clock64 stamps of CTA (cta,0,0) of subsequent launches into a device buffer of >= 16 int64; NULL disables
+CDSEG_API void cdseg_gemm_tc_set_trace(long long* buf, int cta) { g_trace = buf; g_trace_cta = cta; }
+
 CDSEG_API size_t cdseg_gemm_tc_workspace_bytes(int64_t M, int N, int nsplit) {
   return nsplit > 1 ? (size_t)nsplit * M * N * sizeof(float) : 0;
 }
@@ -457,21 +497,28 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   const int SB = iters >= 4 ? (un_max <= 64 ? 4 : 3) : 2;
   const size_t smem = (size_t)gt::STG_BYTES + (size_t)SB * 2 * b_bytes + sizeof(gt::Bars) + 64 +
                       ((idx && T <= 32) ? (size_t)gt::BM * T * 4 : 0) + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(gt::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // two register budgets: 3+ CTAs per SM (<= 112 registers, a few spills) when TMEM and shared memory allow that many,
+  // otherwise the spill-free 2-per-SM build.  CDSEG_GEMM_MINB=2|3 forces one for experiments.
+  static const int forced = [] { const char* e = getenv("CDSEG_GEMM_MINB"); return e ? atoi(e) : 0; }();
+  const bool dense3 = forced ? forced == 3 : (tmem_cols <= 128 && smem * 3 <= 220 * 1024);
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[dense3]) {
+    cudaError_t e = dense3 ? cudaFuncSetAttribute(gt::gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(gt::gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
+    configured[dense3] = smem;
   }
   gt::Params p;
   p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp;
   p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.ldr = ldr; p.act = act; p.out = out; p.ldo = ldo;
   p.part = (float*)workspace; p.nsplit = nsplit;
   p.AT = AT; p.SB = SB; p.b_bytes = b_bytes; p.acc_cols = acc_cols; p.tmem_cols = tmem_cols;
+  p.trace = g_trace; p.trace_cta = g_trace_cta;
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + gt::NT - 1) / gt::NT, nsplit);
-  gt::gemm_tc_kernel<<<g, gt::NTHREADS, smem, st>>>(p);
+  if (dense3) gt::gemm_tc_kernel<3><<<g, gt::NTHREADS, smem, st>>>(p);
+  else gt::gemm_tc_kernel<2><<<g, gt::NTHREADS, smem, st>>>(p);
   CDSEG_COUNT_LAUNCH(1);
   if (nsplit > 1) {
     gt::splitk_reduce_kernel<<<cdseg_div_up(M * N, 256), 256, 0, st>>>((const float*)workspace, nsplit, M, N, bias, res,

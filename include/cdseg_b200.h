@@ -130,6 +130,8 @@ int cdseg_tile_tap_mask(const int32_t* nbr, int64_t M, int T, uint32_t* mask, vo
 /* out[M,N] = act(bias + sum_t A[idx[m,t]] @ W_t) + res ; idx NULL => row m, tap t = its t-th K-slice (split-K Linear); tile_mask NULL => all
  * taps; act 0 none / 1 GELU(erf); nsplit > 1 splits the taps over grid.z (partials in workspace, reduced by a 2nd kernel) */
 size_t cdseg_gemm_tc_workspace_bytes(int64_t M, int N, int nsplit);
+/* profiling hook: clock64 stamps of CTA (cta,0,0) of subsequent launches into a device buffer of >= 16 int64; NULL disables */
+void cdseg_gemm_tc_set_trace(long long* buf, int cta);
 int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int T, const uint32_t* tile_mask, const float* Bp,
                   int64_t M, int N, int K, const float* bias, const float* res, int64_t ldr, int act, float* out,
                   int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes, void* stream);
