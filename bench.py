@@ -229,9 +229,8 @@ def run_cuda(args):
     #  * dominant kernel by device time = gt::gemm_tc_kernel (profiles/): a skinny, HBM-bound GEMM.  Representative launch:
     #    the stage-0 MLP fc1 (120k x 32 -> 128, bias + GELU fused).  Algorithmic bytes = read A (n*C*4) + write out
     #    (n*4C*4) + packed weights (read once).
-    #  * the one dense contraction north_star names = tc::attn_tc_kernel at stage 0 (tensor/MUFU bound).
-    roof = attn = None
-    if prof:
+    #  * the one dense contraction north_star names = tc2::attn_tc2_kernel at stage 0 (tensor/MUFU bound).
+    def kernel_lines(prof, steps):
         lib = ops._lib.load()
         import ctypes
 
@@ -246,17 +245,32 @@ def run_cuda(args):
         p0 = sel[0]
         fl = 4.0 * p0["pairs"] * p0["C"]
         ex = p0["pairs"] * p0["H"]
-        attn = {"bound": "tensor", "kernel": "tc::attn_tc_kernel (stage 0, %d launches/step)" % (len(sel) // args.steps),
+        attn = {"bound": "tensor", "kernel": "tc2::attn_tc2_kernel (stage 0, %d launches/step)" % (len(sel) // steps),
                 "achieved": fl / (t_attn * 1e-3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s", "frac": fl / (t_attn * 1e-3) / 1e12 / tf_sust,
                 "flops_per_launch": fl, "ms_per_launch": t_attn, "exp_per_launch": ex, "gexp_per_s": ex / (t_attn * 1e-3) / 1e9,
                 "mufu_peak_gexp_per_s": 148 * 16 * 1.965, "traffic": None}
         by = p0["n"] * p0["C"] * 4 + p0["n"] * 4 * p0["C"] * 4 + 2 * 4 * p0["C"] * p0["C"] * 2
-        roof = {"bound": "hbm", "kernel": "gt::gemm_tc_kernel (stage-0 MLP fc1 120000x32->128 + GELU, %d launches/step)" % (len(sel) // args.steps),
+        roof = {"bound": "hbm", "kernel": "gt::gemm_tc_kernel (stage-0 MLP fc1 120000x32->128 + GELU, %d launches/step)" % (len(sel) // steps),
                 "achieved": by / (t_fc1 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / (t_fc1 * 1e-3) / 1e9 / hbm,
                 "peak_source": which, "bytes_per_launch": by, "ms_per_launch": t_fc1, "traffic": None}
         for p in prof:
             for e in p["ev"]:
                 lib.cdseg_event_destroy(e)
+        return roof, attn
+
+    roof = attn = None
+    if prof:
+        roof, attn = kernel_lines(prof, args.steps)
+        # In the timed region above the Noise Network runs on a second stream beside the Conditional Network, so the
+        # events around one launch also cover whatever the other stream had resident.  A few extra steps with the
+        # two-stream schedule switched off give the same launches alone on the device (reported next to the in-step time).
+        seg.backbone.overlap_streams = False
+        k1 = max(2, min(5, args.steps))
+        _, _, _, prof1 = timed(step_resident, k1, 1, profile_attn=True)
+        seg.backbone.overlap_streams = True
+        r1, a1 = kernel_lines(prof1, k1)
+        for full, alone in ((roof, r1), (attn, a1)):
+            full["single_stream"] = {"ms_per_launch": alone["ms_per_launch"], "achieved": alone["achieved"], "frac": alone["frac"]}
 
     line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
