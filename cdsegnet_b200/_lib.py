@@ -117,6 +117,7 @@ SIGNATURES = {
     "cdseg_event_create": (_P, []),
     "cdseg_event_destroy": (None, [_P]),
     "cdseg_event_elapsed_ms": (_I, [_P, _P, ctypes.POINTER(_F)]),
+    "cdseg_conv_im2col_tc": (_I, [_P, _P, _I, _P, _L, _I, _P, _I, _P, _L, _P]),
     "cdseg_gemm_tc": (_I, [_P, _L, _P, _I, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P, _L, _I, _P, _Z, _P]),
 }
 

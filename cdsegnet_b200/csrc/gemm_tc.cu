@@ -95,6 +95,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 struct Params {
   const float* A; long long lda;
   const int32_t* idx; int T;              // idx [M, T] (row of A feeding tap t); null => row m, tap t = columns [tK, (t+1)K)
+  int sub, taps_ld;                       // sub = 4: im2col mode, iteration t = taps 4t..4t+3 x 8 channels of idx [M, taps_ld]
   const uint32_t* tile_mask;              // per 128-row tile: bit t set <=> some row has tap t ; null => all taps
   const float* Bp;                        // packed weights [T][K/KC][ntiles][2][NT*KC]
   int M, N, K;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
     // this tile's neighbour indices, staged once in shared memory (one coalesced block read) so that the per-tap
     // row address no longer hangs off a dependent global load
     int32_t* s_idx = reinterpret_cast<int32_t*>(s_b + (size_t)SB * 2 * B_BYTES + sizeof(Bars) + 64);
-    const bool idx_smem = p.idx != nullptr && p.T <= 32;
+    const bool idx_smem = p.idx != nullptr && p.T <= 32 && !p.sub;
     if (idx_smem) {
       const long long base = (long long)tile_m * BM * p.T, total = (long long)p.M * p.T;
       for (int j = r; j < BM * p.T; j += 128) s_idx[j] = base + j < total ? __ldg(p.idx + base + j) : -1;
@@ -208,6 +209,21 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
     }
     auto fetch = [&](int it, float4* v) {
       const int t = tap_of(it), kc = it - (it / kch) * kch;
+      if (p.sub) {
+        // im2col chunk (tiny C_in, padded to 8): K = 32 = 4 taps x 8 channels, each tap a 32-byte row of A
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tap = t * 4 + q;
+          const int s8 = (row_ok && tap < p.taps_ld) ? __ldg(p.idx + m * p.taps_ld + tap) : -1;
+          if (s8 >= 0) {
+            const float4* row = reinterpret_cast<const float4*>(p.A + (long long)s8 * 8);
+            v[2 * q] = __ldg(row); v[2 * q + 1] = __ldg(row + 1);
+          } else {
+            v[2 * q] = v[2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        return;
+      }
       long long src = -1;
       if (idx_smem) src = s_idx[r * p.T + t];
       else if (row_ok) src = p.idx ? (long long)__ldg(p.idx + m * p.T + t) : m;
@@ -476,10 +492,10 @@ CDSEG_API size_t cdseg_gemm_tc_workspace_bytes(int64_t M, int N, int nsplit) {
 }
 
 // out[M,N] = act(bias + sum_t A[idx[:,t]] @ W_t) + res   (see include/cdseg_b200.h)
-CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int T, const uint32_t* tile_mask,
-                            const float* Bp, int64_t M, int N, int K, const float* bias, const float* res, int64_t ldr,
-                            int act, float* out, int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T, const uint32_t* tile_mask,
+                          const float* Bp, int64_t M, int N, int K, const float* bias, const float* res, int64_t ldr,
+                          int act, float* out, int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes,
+                          void* stream, int sub, int taps_ld) {
   cudaStream_t st = (cudaStream_t)stream;
   if (M < 0 || N <= 0 || K <= 0 || (K % 16) || (lda & 3) || T <= 0 ||
       nsplit < 1 || nsplit > T || (tile_mask && T > 32))
@@ -496,7 +512,7 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   while (tmem_cols < acc_cols + AT * 32) tmem_cols <<= 1;
   const int SB = iters >= 4 ? (un_max <= 64 ? 4 : 3) : 2;
   const size_t smem = (size_t)gt::STG_BYTES + (size_t)SB * 2 * b_bytes + sizeof(gt::Bars) + 64 +
-                      ((idx && T <= 32) ? (size_t)gt::BM * T * 4 : 0) + 1024;
+                      ((idx && T <= 32 && !sub) ? (size_t)gt::BM * T * 4 : 0) + 1024;
   // two register budgets: 3+ CTAs per SM (<= 112 registers, a few spills) when TMEM and shared memory allow that many,
   // otherwise the spill-free 2-per-SM build.  CDSEG_GEMM_MINB=2|3 forces one for experiments.
   static const int forced = [] { const char* e = getenv("CDSEG_GEMM_MINB"); return e ? atoi(e) : 0; }();
@@ -509,7 +525,7 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
     configured[dense3] = smem;
   }
   gt::Params p;
-  p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp;
+  p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp; p.sub = sub; p.taps_ld = taps_ld;
   p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.ldr = ldr; p.act = act; p.out = out; p.ldo = ldo;
   p.part = (float*)workspace; p.nsplit = nsplit;
   p.AT = AT; p.SB = SB; p.b_bytes = b_bytes; p.acc_cols = acc_cols; p.tmem_cols = tmem_cols;
@@ -527,4 +543,23 @@ CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int
   }
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;
+}
+
+CDSEG_API int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int T, const uint32_t* tile_mask,
+                            const float* Bp, int64_t M, int N, int K, const float* bias, const float* res, int64_t ldr,
+                            int act, float* out, int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  return gemm_tc_launch(A, lda, idx, T, tile_mask, Bp, M, N, K, bias, res, ldr, act, out, ldo, nsplit, workspace,
+                        workspace_bytes, stream, 0, 0);
+}
+
+// Sparse conv with a tiny C_in (the k=5 stem, 6 input channels) as an im2col GEMM on the tensor cores:
+// A8 [rows, 8] = input padded to 8 channels, nbr [M, taps], Bp = cdseg_gemm_pack_b of [ceil(taps/4)][32][N] where row
+// 8*q + c of block t holds the weight of tap 4t+q, channel c (zero for c >= C_in or tap >= taps).
+// out = act(bias + conv) -- eval-BatchNorm folded into Bp / bias by the caller (see include/cdseg_b200.h).
+CDSEG_API int cdseg_conv_im2col_tc(const float* A8, const int32_t* nbr, int taps, const float* Bp, int64_t M, int N,
+                                   const float* bias, int act, float* out, int64_t ldo, void* stream) {
+  if (!nbr || taps <= 0) return CDSEG_EINVAL;
+  return gemm_tc_launch(A8, 8, nbr, (taps + 3) / 4, nullptr, Bp, M, N, 32, bias, nullptr, 0, act, out, ldo, 1, nullptr, 0,
+                        stream, 4, taps);
 }

@@ -192,6 +192,15 @@ def subm_conv(x, nbr, wt, bias, ksize, ep_scale=None, ep_shift=None, ep_gelu=Fal
     return out
 
 
+def conv_im2col_tc(x8, nbr, Bp, N, bias, act):
+    """tiny-C_in sparse conv as an im2col GEMM (x8: fp32 [n, 8] zero-padded input, nbr int32 [n, taps])."""
+    n = nbr.shape[0]
+    out = torch.empty((n, N), dtype=torch.float32, device=x8.device)
+    check(_lib.load().cdseg_conv_im2col_tc(_p(x8, torch.float32), _p(nbr, torch.int32), nbr.shape[1], _p(Bp, torch.float32),
+                                           n, N, _p(bias), act, _p(out), N, _stream()), "conv_im2col_tc")
+    return out
+
+
 # ---------------------------------------------------------------- attention
 ATTN_V2 = True        # tcgen05 attention generation: True = attn_tc2.cu (streamed K/V, merged [V|1] operand), False = attn_tc.cu
 

@@ -367,7 +367,19 @@ class Embedding(nn.Module):
         level = point["_level"]
         scale, shift = bn_fold(self.stem.norm)
         conv = self.stem.conv
-        if conv.cin <= 8:
+        if conv.cin <= 8 and ops.GEMM_MODE == "tc":
+            # im2col GEMM on the tensor cores: K = 4 taps x 8 (zero-padded) channels per step, BN folded into W / bias
+            def build():
+                k3 = conv.k ** 3
+                w = conv.wt() * scale                                      # [k3, cin, cout]
+                wp = w.new_zeros((-(-k3 // 4) * 4, 8, conv.cout))
+                wp[:k3, : conv.cin] = w
+                return ops.gemm_pack_b(wp.reshape(-1, 32, conv.cout))
+            bn = self.stem.norm
+            Bp = _PACK.get((id(conv.weight), "stem"), [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var], build)
+            x8 = F.pad(point["feat"].float(), (0, 8 - conv.cin))
+            point["feat"] = ops.conv_im2col_tc(x8, level.nbr(conv.k), Bp, conv.cout, shift, 1)
+        elif conv.cin <= 8:
             point["feat"] = conv(point["feat"], level, scale, shift, True)
         else:
             point["feat"] = ops.scale_shift_act(conv(point["feat"], level), scale, shift, 1)

@@ -135,6 +135,12 @@ void cdseg_gemm_tc_set_trace(long long* buf, int cta);
 int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int T, const uint32_t* tile_mask, const float* Bp,
                   int64_t M, int N, int K, const float* bias, const float* res, int64_t ldr, int act, float* out,
                   int64_t ldo, int nsplit, void* workspace, size_t workspace_bytes, void* stream);
+/* Embedding stem (ptv3.py:633-663: spconv.SubMConv3d k=5, C_in=6, bias=False + BatchNorm1d(eval) + GELU) as an im2col
+ * GEMM on the tensor cores: A8 fp32 [rows,8] = input zero-padded to 8 channels; nbr int32 [M,taps]; Bp = cdseg_gemm_pack_b
+ * of W [ceil(taps/4)][32][N] whose row 8q+c of block t is the (BN-scaled) weight of tap 4t+q, channel c (zero padding);
+ * out[M,N] = act(bias + conv) with bias = the folded BN shift */
+int cdseg_conv_im2col_tc(const float* A8, const int32_t* nbr, int taps, const float* Bp, int64_t M, int N,
+                         const float* bias, int act, float* out, int64_t ldo, void* stream);
 
 /* ---- native executor of one PTv3 Block (ptv3.py:399-428): the 12-13 launches above enqueued from C++ in one call --- */
 typedef struct CdsegBlockArgs {

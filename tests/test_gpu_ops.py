@@ -335,3 +335,25 @@ def test_gemm_tc_conv_vs_oracle(ops, c, ns):
     out = ops.gemm_tc(x.to(DEV), Bp, c, c, idx=nbr, tile_mask=mask, bias=bias.to(DEV), nsplit=ns)
     torch.cuda.synchronize()
     assert (out.cpu() - ref).abs().max() < 1e-4      # 3xTF32: ~2^-21 relative per product, |out| up to ~5
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("ci,co", [(6, 32), (4, 32), (6, 48)])
+def test_stem_conv_im2col_tc_vs_oracle(ops, ci, co):
+    """Embedding stem (k=5, tiny C_in) through the tensor-core im2col GEMM == oracle conv + folded BN + exact GELU"""
+    sc = _scene((1500, 700))
+    g, b = sc["grid_coord"], S.offset2batch(sc["offset"])
+    gen = torch.Generator().manual_seed(ci * 7 + co)
+    x = torch.randn(len(g), ci, generator=gen)
+    w = torch.randn(co, 5, 5, 5, ci, generator=gen) / (125 * ci * 0.4) ** 0.5
+    scale, shift = torch.rand(co, generator=gen) + 0.5, torch.randn(co, generator=gen)
+    ref = torch.nn.functional.gelu(O.subm_conv3d(x, torch.from_numpy(b), torch.from_numpy(g), w, None) * scale + shift)
+    nbr = ops.nbr_build(cu(g), cu(b, torch.int32), 5)
+    wt = w.reshape(co, 125, ci).permute(1, 2, 0) * scale                      # [125, ci, co]
+    wp = torch.zeros(128, 8, co)
+    wp[:125, :ci] = wt
+    Bp = ops.gemm_pack_b(wp.reshape(32, 32, co).contiguous().to(DEV))
+    x8 = torch.nn.functional.pad(x, (0, 8 - ci)).to(DEV)
+    out = ops.conv_im2col_tc(x8, nbr, Bp, co, shift.to(DEV), 1)
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max() < 1e-4
