@@ -20,6 +20,9 @@ static int pick_split(int64_t tiles, int T) {
 
 struct Gemm { const float* Bp; const float* bias; };
 
+static int g_fused_mask = 0x7fffffff;
+CDSEG_API void cdseg_set_fused_mask(int mask) { g_fused_mask = mask; }
+
 // one Linear through cdseg_gemm_tc with the same split heuristic as the Python path (cdsegnet_b200/ptv3.py::linear)
 static int run_linear(const float* x, int64_t n, int K, int N, const float* Bp, const float* bias, const float* res, int act,
                       float* out, void* ws, size_t ws_bytes, void* stream) {
@@ -89,6 +92,14 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
   if (a->ev[0]) cudaEventRecord((cudaEvent_t)a->ev[0], (cudaStream_t)stream);
   RUN(cdseg_attn_tc2(qp, kp, vp, a->patch_len, a->slot_dst, a->H, a->T, a->Kp, a->scale, o, C, stream));
   if (a->ev[1]) cudaEventRecord((cudaEvent_t)a->ev[1], (cudaStream_t)stream);
+  if ((g_fused_mask & 1) && (C == 32 || C == 64 || C == 128)) {
+    // proj + residual + norm2 + MLP + residual: one kernel, intermediates in tensor memory (fused_post.cu)
+    if (a->ev[2]) cudaEventRecord((cudaEvent_t)a->ev[2], (cudaStream_t)stream);
+    RUN(cdseg_post_attn(o, x1, n, C, a->proj_Bp, a->proj_b, a->n2_g, a->n2_b, a->ln_eps, a->fc1_Bp, a->fc1_b, a->fc2_Bp,
+                        a->fc2_b, a->out, stream));
+    if (a->ev[3]) cudaEventRecord((cudaEvent_t)a->ev[3], (cudaStream_t)stream);
+    return CDSEG_OK;
+  }
   RUN(run_linear(o, n, C, C, a->proj_Bp, a->proj_b, nullptr, 0, att, ws, ws_bytes, stream));
   // residual + norm2 + MLP (fc1+GELU, fc2+residual fused in the GEMM epilogues)
   RUN(cdseg_add_layernorm(x1, att, nullptr, nullptr, a->n2_g, a->n2_b, a->ln_eps, n, C, y2, h, stream));

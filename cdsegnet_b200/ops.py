@@ -292,6 +292,19 @@ def tile_tap_mask(nbr):
     return mask
 
 
+def post_attn(o, x1, proj, ln, fc1, fc2, eps=1e-5):
+    """x2 = x1 + proj(o); out = x2 + fc2(GELU(fc1(LN(x2)))) in one kernel.  proj/fc1/fc2 = (packed blocks, bias); ln = (gamma, beta)"""
+    n, C = o.shape
+    out = torch.empty_like(o)
+    check(_lib.load().cdseg_post_attn(_p(o, torch.float32), _p(x1, torch.float32), n, C, _p(proj[0]), _p(proj[1]), _p(ln[0]), _p(ln[1]),
+                                      float(eps), _p(fc1[0]), _p(fc1[1]), _p(fc2[0]), _p(fc2[1]), _p(out), _stream()), "post_attn")
+    return out
+
+
+def set_fused_mask(mask):
+    _lib.load().cdseg_set_fused_mask(int(mask))
+
+
 GEMM_MODE = "tc"      # "tc": tcgen05 split-fp16 kernels for conv + linears ; "simt": round-1a SIMT conv + cuBLAS SGEMM
 NATIVE_BLOCKS = True  # run each PTv3 Block through the C++ executor (cdseg_block_forward) instead of launch-by-launch
 

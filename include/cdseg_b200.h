@@ -142,6 +142,15 @@ int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int T, const 
 int cdseg_conv_im2col_tc(const float* A8, const int32_t* nbr, int taps, const float* Bp, int64_t M, int N,
                          const float* bias, int act, float* out, int64_t ldo, void* stream);
 
+/* ---- fused row-tile kernels (C = 32 / 64 / 128): chained skinny GEMMs whose intermediates stay in tensor memory ------
+ * post-attention half of a Block, ptv3.py:290-296 + 416-424:  x2 = x1 + proj(o) + b ; out = x2 + fc2(GELU(fc1(LayerNorm(x2))))
+ * o, x1, out: fp32 [n, C] contiguous, 16-byte aligned; *_Bp = cdseg_gemm_pack_b of W^T ([1][C][C], [1][C][4C], [1][4C][C]) */
+int cdseg_post_attn(const float* o, const float* x1, int64_t n, int C, const float* proj_Bp, const float* proj_b,
+                    const float* ln_g, const float* ln_b, float eps, const float* fc1_Bp, const float* fc1_b,
+                    const float* fc2_Bp, const float* fc2_b, float* out, void* stream);
+/* which fused kernels cdseg_block_forward uses: bit 0 post-attention chain (default: all that exist) */
+void cdseg_set_fused_mask(int mask);
+
 /* ---- native executor of one PTv3 Block (ptv3.py:399-428): the 12-13 launches above enqueued from C++ in one call --- */
 typedef struct CdsegBlockArgs {
   int64_t n; int C, H, T_dim, B;                 /* points, channels, heads (C = 16 H), timestep width, scenes */

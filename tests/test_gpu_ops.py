@@ -357,3 +357,27 @@ def test_stem_conv_im2col_tc_vs_oracle(ops, ci, co):
     out = ops.conv_im2col_tc(x8, nbr, Bp, co, shift.to(DEV), 1)
     torch.cuda.synchronize()
     assert (out.cpu() - ref).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------ fused row-tile kernels (chained GEMMs in tensor memory)
+def _lin(gen, cin, cout):
+    return torch.randn(cout, cin, generator=gen) / cin ** 0.5, 0.3 * torch.randn(cout, generator=gen)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("n,C", [(1000, 32), (128, 32), (1, 32), (5000, 64), (777, 128), (40000, 32), (33000, 64), (20000, 128)])
+def test_post_attn_chain_vs_fp64(ops, n, C):
+    """proj + residual + LayerNorm + fc1 + GELU + fc2 + residual in ONE kernel == the fp64 composition (ptv3.py:290-296, 416-424)"""
+    gen = torch.Generator().manual_seed(n + C)
+    o, x1 = torch.randn(n, C, generator=gen), 2.0 * torch.randn(n, C, generator=gen) + 0.5
+    wp, bp = _lin(gen, C, C); w1, b1 = _lin(gen, C, 4 * C); w2, b2 = _lin(gen, 4 * C, C)
+    g, be = torch.rand(C, generator=gen) + 0.5, 0.2 * torch.randn(C, generator=gen)
+    d = lambda a: a.double()
+    x2 = d(x1) + d(o) @ d(wp).t() + d(bp)
+    h = torch.nn.functional.layer_norm(x2, (C,), d(g), d(be), 1e-5)
+    ref = x2 + torch.nn.functional.gelu(h @ d(w1).t() + d(b1)) @ d(w2).t() + d(b2)
+    pk = lambda w, b: (ops.gemm_pack_b(w.t().contiguous()[None].to(DEV)), b.to(DEV))
+    out = ops.post_attn(o.to(DEV), x1.to(DEV), pk(wp, bp), (g.to(DEV), be.to(DEV)), pk(w1, b1), pk(w2, b2), 1e-5)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
