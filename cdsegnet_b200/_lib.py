@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
-SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "fused_post.cu", "block_exec.cu"]
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
@@ -113,6 +113,7 @@ SIGNATURES = {
     "cdseg_gemm_tc_workspace_bytes": (_Z, [_L, _I, _I]),
     "cdseg_gemm_tc_set_trace": (None, [_P, _I]),
     "cdseg_post_attn": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
+    "cdseg_pre_attn": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
     "cdseg_set_fused_mask": (None, [_I]),
     "cdseg_block_scratch_bytes": (_Z, [_L, _I, _I, _I, _I, _I]),
     "cdseg_block_forward": (_I, [ctypes.POINTER(BlockArgs), _P]),

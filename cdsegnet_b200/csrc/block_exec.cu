@@ -69,6 +69,18 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
   const size_t ws_bytes = (size_t)(end - p);
   int st;
 #define RUN(call) do { st = (call); if (st != CDSEG_OK) return st; } while (0)
+  const bool fused_c = C == 32 || C == 64 || C == 128;
+  if ((g_fused_mask & 2) && fused_c) {
+    // cpe conv + Linear + LayerNorm + residual (+ t) + norm1 + qkv: one kernel (fused_pre.cu)
+    const float* tp = nullptr;
+    if (a->t_scene) {
+      RUN(cdseg_small_linear(a->t_scene, a->t_W, a->t_b, 0, a->B, a->T_dim, C, tproj, stream));
+      tp = tproj;
+    }
+    RUN(cdseg_pre_attn(a->conv_in ? a->conv_in : a->x, a->x, n, C, a->nbr, a->tile_mask, a->conv_Bp, a->conv_b, a->lin_Bp, a->lin_b,
+                       a->cpe_g, a->cpe_b, tp, tp ? a->batch : nullptr, a->n1_g, a->n1_b, a->ln_eps, a->qkv_Bp, a->qkv_b, x1, qkv,
+                       stream));
+  } else {
   // cpe: conv (implicit GEMM over 27 taps) -> Linear -> LayerNorm
   {
     const int64_t tiles = ((n + 127) / 128) * ((C + 127) / 128);
@@ -88,11 +100,12 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
   RUN(cdseg_add_layernorm(a->x, y1, tp, tp ? a->batch : nullptr, a->n1_g, a->n1_b, a->ln_eps, n, C, x1, h, stream));
   // attention
   RUN(run_linear(h, n, C, 3 * C, a->qkv_Bp, a->qkv_b, nullptr, 0, qkv, ws, ws_bytes, stream));
+  }
   RUN(cdseg_attn_pack_f16v(qkv, 3 * C, 0, C, 3, a->slot_src, a->H, a->T, a->Kp, qp, kp, vp, 1, stream));
   if (a->ev[0]) cudaEventRecord((cudaEvent_t)a->ev[0], (cudaStream_t)stream);
   RUN(cdseg_attn_tc2(qp, kp, vp, a->patch_len, a->slot_dst, a->H, a->T, a->Kp, a->scale, o, C, stream));
   if (a->ev[1]) cudaEventRecord((cudaEvent_t)a->ev[1], (cudaStream_t)stream);
-  if ((g_fused_mask & 1) && (C == 32 || C == 64 || C == 128)) {
+  if ((g_fused_mask & 1) && fused_c) {
     // proj + residual + norm2 + MLP + residual: one kernel, intermediates in tensor memory (fused_post.cu)
     if (a->ev[2]) cudaEventRecord((cudaEvent_t)a->ev[2], (cudaStream_t)stream);
     RUN(cdseg_post_attn(o, x1, n, C, a->proj_Bp, a->proj_b, a->n2_g, a->n2_b, a->ln_eps, a->fc1_Bp, a->fc1_b, a->fc2_Bp,

@@ -148,7 +148,15 @@ int cdseg_conv_im2col_tc(const float* A8, const int32_t* nbr, int taps, const fl
 int cdseg_post_attn(const float* o, const float* x1, int64_t n, int C, const float* proj_Bp, const float* proj_b,
                     const float* ln_g, const float* ln_b, float eps, const float* fc1_Bp, const float* fc1_b,
                     const float* fc2_Bp, const float* fc2_b, float* out, void* stream);
-/* which fused kernels cdseg_block_forward uses: bit 0 post-attention chain (default: all that exist) */
+/* pre-attention half of a Block, ptv3.py:355-362 + 400-413 + 258:  x1 = x + LayerNorm_cpe(Linear(SubMConv3d_k3(conv_in))) (+ tproj[batch]) ;
+ * qkv = Linear_qkv(LayerNorm_1(x1)).  conv_in, x, x1: fp32 [n, C]; qkv: fp32 [n, 3C]; nbr int32 [n, 27] + tile_mask from
+ * cdseg_nbr_build / cdseg_tile_tap_mask; conv_Bp = cdseg_gemm_pack_b of the tap-major weight [27][C][C]; lin_Bp / qkv_Bp of W^T;
+ * tproj fp32 [B, C] (per-scene t_mlp output) + batch int32 [n], or NULL for the Conditional Network */
+int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, int C, const int32_t* nbr, const uint32_t* tile_mask,
+                   const float* conv_Bp, const float* conv_b, const float* lin_Bp, const float* lin_b, const float* cpe_g,
+                   const float* cpe_b, const float* tproj, const int32_t* batch, const float* n1_g, const float* n1_b,
+                   float eps, const float* qkv_Bp, const float* qkv_b, float* x1, float* qkv, void* stream);
+/* which fused kernels cdseg_block_forward uses: bit 0 post-attention chain, bit 1 pre-attention chain (default: all) */
 void cdseg_set_fused_mask(int mask);
 
 /* ---- native executor of one PTv3 Block (ptv3.py:399-428): the 12-13 launches above enqueued from C++ in one call --- */

@@ -46,3 +46,39 @@ for n, C in ((120000, 32), (120000, 64), (52190, 64), (14640, 128), (14640, 64))
         t_old, t_new = timeit(old, cold), timeit(new, cold)
         print(f"post_attn n={n} C={C} {'cold' if cold else 'warm'}: 4 launches {t_old:7.1f} us -> fused {t_new:7.1f} us "
               f"({alg / t_new * 1e-3:6.0f} GB/s algorithmic, max|old-new| {err:.1e})")
+
+
+# ---- pre-attention chain on a real neighbour table
+import numpy as np
+import bench
+sc = bench.make_scene(0)
+grid = torch.from_numpy(np.ascontiguousarray(sc["grid_coord"])).int().to(dev)
+n = grid.shape[0]
+batch = torch.zeros(n, dtype=torch.int32, device=dev)
+# curve order first, like the model does internally (rows of a tile are spatial neighbours)
+codes = ops.encode_codes(grid, batch, 9, ["z"])
+order, _ = ops.argsort_rows(codes, 27)
+grid = grid[order[0].long()].contiguous()
+nbr = ops.nbr_build(grid, batch, 3)
+mask = ops.tile_tap_mask(nbr)
+for C in (32, 64):
+    x = torch.randn(n, C, device=dev)
+    wc = torch.randn(27, C, C, device=dev) / (27 * C * 0.4) ** 0.5
+    conv = (ops.gemm_pack_b(wc), torch.randn(C, device=dev))
+    l1, qk = lin(C, C), lin(C, 3 * C)
+    cg, cb, g1, b1 = (torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev), torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev))
+
+    def old():
+        y = ops.gemm_tc(x, conv[0], C, C, idx=nbr, tile_mask=mask, bias=conv[1])
+        y = ops.gemm_tc(y, l1[0], C, C, bias=l1[1])
+        _, y = ops.add_layernorm(y, gamma=cg, beta=cb, want_sum=False)
+        x1, h = ops.add_layernorm(x, y, gamma=g1, beta=b1)
+        return x1, ops.gemm_tc(h, qk[0], 3 * C, C, bias=qk[1])
+
+    def new():
+        return ops.pre_attn(x, x, nbr, mask, conv, l1, (cg, cb), (g1, b1), qk)
+    (a1, aq), (b1_, bq) = old(), new()
+    err = max((a1 - b1_).abs().max().item(), (aq - bq).abs().max().item())
+    for cold in (False, True):
+        t_old, t_new = timeit(old, cold), timeit(new, cold)
+        print(f"pre_attn n={n} C={C} {'cold' if cold else 'warm'}: 5 launches {t_old:7.1f} us -> fused {t_new:7.1f} us (max|old-new| {err:.1e})")

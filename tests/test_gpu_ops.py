@@ -381,3 +381,39 @@ def test_post_attn_chain_vs_fp64(ops, n, C):
     torch.cuda.synchronize()
     err = (out.cpu().double() - ref).abs().max().item()
     assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("counts,C,with_t,stale", [((1500, 600), 32, False, False), ((1500, 600), 32, True, True), ((3000,), 64, True, False),
+                                                    ((900, 500), 128, False, True), ((130,), 64, False, False)])
+def test_pre_attn_chain_vs_fp64(ops, counts, C, with_t, stale):
+    """cpe conv + Linear + LayerNorm + residual (+ per-scene t) + norm1 + qkv in ONE kernel == the fp64 composition
+    (ptv3.py:355-362, 400-413, 258); `stale` = the conv reads another tensor than the residual (unpooling quirk)"""
+    sc = _scene(counts)
+    g, b = sc["grid_coord"], S.offset2batch(sc["offset"])
+    n = len(g)
+    gen = torch.Generator().manual_seed(C + n)
+    x = torch.randn(n, C, generator=gen)
+    cin = torch.randn(n, C, generator=gen) if stale else x
+    wc = torch.randn(C, 3, 3, 3, C, generator=gen) / (27 * C * 0.4) ** 0.5
+    bc = 0.3 * torch.randn(C, generator=gen)
+    wl, bl = _lin(gen, C, C); wq, bq = _lin(gen, C, 3 * C)
+    cg, cb = torch.rand(C, generator=gen) + 0.5, 0.2 * torch.randn(C, generator=gen)
+    g1, b1 = torch.rand(C, generator=gen) + 0.5, 0.2 * torch.randn(C, generator=gen)
+    tproj = torch.randn(len(counts), C, generator=gen) if with_t else None
+    d = lambda a: a.double()
+    y = O.subm_conv3d(d(cin), torch.from_numpy(b), torch.from_numpy(g), d(wc), d(bc))
+    y = torch.nn.functional.layer_norm(y @ d(wl).t() + d(bl), (C,), d(cg), d(cb), 1e-5)
+    x1 = d(x) + y + (d(tproj)[torch.from_numpy(b).long()] if with_t else 0)
+    qkv = torch.nn.functional.layer_norm(x1, (C,), d(g1), d(b1), 1e-5) @ d(wq).t() + d(bq)
+    nbr = ops.nbr_build(cu(g), cu(b, torch.int32), 3)
+    mask = ops.tile_tap_mask(nbr)
+    pk = lambda w, bb: (ops.gemm_pack_b(w.t().contiguous()[None].to(DEV)), bb.to(DEV))
+    conv = (ops.gemm_pack_b(wc.reshape(C, 27, C).permute(1, 2, 0).contiguous().to(DEV)), bc.to(DEV))
+    o1, oq = ops.pre_attn(cin.to(DEV), x.to(DEV), nbr, mask, conv, pk(wl, bl), (cg.to(DEV), cb.to(DEV)), (g1.to(DEV), b1.to(DEV)),
+                          pk(wq, bq), tproj.to(DEV) if with_t else None, cu(b, torch.int32) if with_t else None, 1e-5)
+    torch.cuda.synchronize()
+    e1 = (o1.cpu().double() - x1).abs().max().item()
+    eq = (oq.cpu().double() - qkv).abs().max().item()
+    assert e1 < 3e-5 * max(1.0, x1.abs().max().item()), e1
+    assert eq < 5e-5 * max(1.0, qkv.abs().max().item()), eq
