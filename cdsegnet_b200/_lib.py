@@ -67,7 +67,7 @@ _Z = ctypes.c_size_t
 class BlockArgs(ctypes.Structure):
     """mirror of CdsegBlockArgs (include/cdseg_b200.h)"""
     _fields_ = [("n", ctypes.c_int64), ("C", _I), ("H", _I), ("T_dim", _I), ("B", _I),
-                ("x", _P), ("conv_in", _P), ("nbr", _P), ("tile_mask", _P), ("batch", _P), ("t_scene", _P),
+                ("x", _P), ("conv_in", _P), ("nbr", _P), ("tile_mask", _P), ("batch", _P), ("conv_plan", _P), ("t_scene", _P),
                 ("slot_src", _P), ("slot_dst", _P), ("patch_len", _P), ("T", _I), ("Kp", _I), ("scale", _F),
                 ("conv_Bp", _P), ("conv_b", _P), ("lin_Bp", _P), ("lin_b", _P), ("cpe_g", _P), ("cpe_b", _P),
                 ("t_W", _P), ("t_b", _P), ("n1_g", _P), ("n1_b", _P), ("qkv_Bp", _P), ("qkv_b", _P), ("proj_Bp", _P),
@@ -113,7 +113,9 @@ SIGNATURES = {
     "cdseg_gemm_tc_workspace_bytes": (_Z, [_L, _I, _I]),
     "cdseg_gemm_tc_set_trace": (None, [_P, _I]),
     "cdseg_post_attn": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
-    "cdseg_pre_attn": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
+    "cdseg_pre_attn": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
+    "cdseg_conv_plan_bytes": (_Z, [_L]),
+    "cdseg_conv_tile_plan": (_I, [_P, _L, _P, _P]),
     "cdseg_set_fused_mask": (None, [_I]),
     "cdseg_block_scratch_bytes": (_Z, [_L, _I, _I, _I, _I, _I]),
     "cdseg_block_forward": (_I, [ctypes.POINTER(BlockArgs), _P]),

@@ -70,16 +70,16 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
   int st;
 #define RUN(call) do { st = (call); if (st != CDSEG_OK) return st; } while (0)
   const bool fused_c = C == 32 || C == 64 || C == 128;
-  if ((g_fused_mask & 2) && fused_c) {
+  if ((g_fused_mask & 2) && fused_c && a->conv_plan) {
     // cpe conv + Linear + LayerNorm + residual (+ t) + norm1 + qkv: one kernel (fused_pre.cu)
     const float* tp = nullptr;
     if (a->t_scene) {
       RUN(cdseg_small_linear(a->t_scene, a->t_W, a->t_b, 0, a->B, a->T_dim, C, tproj, stream));
       tp = tproj;
     }
-    RUN(cdseg_pre_attn(a->conv_in ? a->conv_in : a->x, a->x, n, C, a->nbr, a->tile_mask, a->conv_Bp, a->conv_b, a->lin_Bp, a->lin_b,
-                       a->cpe_g, a->cpe_b, tp, tp ? a->batch : nullptr, a->n1_g, a->n1_b, a->ln_eps, a->qkv_Bp, a->qkv_b, x1, qkv,
-                       stream));
+    RUN(cdseg_pre_attn(a->conv_in ? a->conv_in : a->x, a->x, n, C, a->nbr, a->tile_mask, a->conv_plan, a->conv_Bp, a->conv_b, a->lin_Bp,
+                       a->lin_b, a->cpe_g, a->cpe_b, tp, tp ? a->batch : nullptr, a->n1_g, a->n1_b, a->ln_eps, a->qkv_Bp, a->qkv_b, x1,
+                       qkv, stream));
   } else {
   // cpe: conv (implicit GEMM over 27 taps) -> Linear -> LayerNorm
   {

@@ -301,14 +301,26 @@ def post_attn(o, x1, proj, ln, fc1, fc2, eps=1e-5):
     return out
 
 
-def pre_attn(conv_in, x, nbr, tile_mask, conv, lin, cpe_ln, n1_ln, qkv, tproj=None, batch=None, eps=1e-5):
+CONV_PLAN_UCAP = 384      # CDSEG_CONV_PLAN_UCAP (include/cdseg_b200.h)
+
+
+def conv_tile_plan(nbr):
+    """per 128-row tile: distinct neighbour rows + local index of every (row, tap) (uint8 records, see the header)"""
+    lib = _lib.load()
+    n = nbr.shape[0]
+    plan = torch.empty(lib.cdseg_conv_plan_bytes(n), dtype=torch.uint8, device=nbr.device)
+    check(lib.cdseg_conv_tile_plan(_p(nbr, torch.int32), n, _p(plan), _stream()), "conv_tile_plan")
+    return plan
+
+
+def pre_attn(conv_in, x, nbr, tile_mask, plan, conv, lin, cpe_ln, n1_ln, qkv, tproj=None, batch=None, eps=1e-5):
     """x1 = x + LN_cpe(lin(conv3(conv_in))) (+ tproj[batch]); qkv = qkv_lin(LN_1(x1)) in one kernel.
     conv/lin/qkv = (packed blocks, bias); *_ln = (gamma, beta).  Returns (x1, qkv)."""
     n, C = x.shape
     x1 = torch.empty_like(x)
     out = torch.empty((n, 3 * C), dtype=torch.float32, device=x.device)
     check(_lib.load().cdseg_pre_attn(_p(conv_in, torch.float32), _p(x, torch.float32), n, C, _p(nbr, torch.int32), _p(tile_mask),
-                                     _p(conv[0]), _p(conv[1]), _p(lin[0]), _p(lin[1]), _p(cpe_ln[0]), _p(cpe_ln[1]), _p(tproj),
+                                     _p(plan, torch.uint8), _p(conv[0]), _p(conv[1]), _p(lin[0]), _p(lin[1]), _p(cpe_ln[0]), _p(cpe_ln[1]), _p(tproj),
                                      _p(batch), _p(n1_ln[0]), _p(n1_ln[1]), float(eps), _p(qkv[0]), _p(qkv[1]), _p(x1), _p(out),
                                      _stream()), "pre_attn")
     return x1, out

@@ -236,6 +236,7 @@ class Block(nn.Module):
         a.n, a.C, a.H, a.T_dim, a.B = n, C, self.attn.num_heads, max(self.T_dim, 0), level.B
         a.x = x.data_ptr(); a.conv_in = conv_in.data_ptr() if conv_in is not None else None
         a.nbr = level.nbr(3).data_ptr(); a.tile_mask = level.tile_mask(3).data_ptr(); a.batch = level.batch.data_ptr()
+        a.conv_plan = level.conv_plan(3).data_ptr() if C in (32, 64, 128) else None
         ts = point.get("t_scene") if self.T_dim != -1 else None
         a.t_scene = ts.data_ptr() if ts is not None else None
         a.slot_src, a.slot_dst, a.patch_len = pm["slot_src"].data_ptr(), pm["slot_dst"].data_ptr(), pm["patch_len"].data_ptr()
@@ -638,7 +639,7 @@ class PointTransformerV3(nn.Module):
         side = self._side_stream(main) if self.overlap_streams else main
         two = side is not main
         if two:
-            nl[0].nbr(5); nl[0].nbr(3); nl[0].tile_mask(3)          # level-0 tables are shared by both branches: build first
+            nl[0].nbr(5); nl[0].nbr(3); nl[0].tile_mask(3); nl[0].conv_plan(3)          # level-0 tables are shared by both branches: build first
             for k in ("feat", "coord", "t_scene", "t_emb"):
                 if k in c and torch.is_tensor(c[k]):
                     c[k].record_stream(side)

@@ -65,6 +65,13 @@ class Level:
             self._nbr[key] = ops.tile_tap_mask(self.nbr(ksize))
         return self._nbr[key]
 
+    def conv_plan(self, ksize):
+        """per 128-row tile: distinct neighbour rows + local indices (operand cache plan of the fused pre-attention kernel)"""
+        key = ("plan", ksize)
+        if key not in self._nbr:
+            self._nbr[key] = ops.conv_tile_plan(self.nbr(ksize))
+        return self._nbr[key]
+
     def patch_maps(self, order_index, K):
         """slot maps of logical curve `order_index`.  Like the reference (ptv3.py:191-244 caches
         "pad"/"unpad" on the Point), the FIRST patch size used at a level sticks."""

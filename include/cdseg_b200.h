@@ -151,11 +151,20 @@ int cdseg_post_attn(const float* o, const float* x1, int64_t n, int C, const flo
 /* pre-attention half of a Block, ptv3.py:355-362 + 400-413 + 258:  x1 = x + LayerNorm_cpe(Linear(SubMConv3d_k3(conv_in))) (+ tproj[batch]) ;
  * qkv = Linear_qkv(LayerNorm_1(x1)).  conv_in, x, x1: fp32 [n, C]; qkv: fp32 [n, 3C]; nbr int32 [n, 27] + tile_mask from
  * cdseg_nbr_build / cdseg_tile_tap_mask; conv_Bp = cdseg_gemm_pack_b of the tap-major weight [27][C][C]; lin_Bp / qkv_Bp of W^T;
- * tproj fp32 [B, C] (per-scene t_mlp output) + batch int32 [n], or NULL for the Conditional Network */
+ * tproj fp32 [B, C] (per-scene t_mlp output) + batch int32 [n], or NULL for the Conditional Network; conv_plan from
+ * cdseg_conv_tile_plan (same nbr) */
 int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, int C, const int32_t* nbr, const uint32_t* tile_mask,
-                   const float* conv_Bp, const float* conv_b, const float* lin_Bp, const float* lin_b, const float* cpe_g,
+                   const void* conv_plan, const float* conv_Bp, const float* conv_b, const float* lin_Bp, const float* lin_b, const float* cpe_g,
                    const float* cpe_b, const float* tproj, const int32_t* batch, const float* n1_g, const float* n1_b,
                    float eps, const float* qkv_Bp, const float* qkv_b, float* x1, float* qkv, void* stream);
+/* Per 128-row tile of a k=3 neighbour table (nbr int32 [n, 27], the spconv `indice_key` rulebook analogue, ptv3.py:356):
+ * the ascending list of DISTINCT neighbour rows of the tile and, for every (row, tap), its index into that list.  One
+ * record of 16 + 4 * CDSEG_CONV_PLAN_UCAP + 128 * 27 * 2 bytes per tile: int32 ucount, int32 pad[3], int32 uniq[UCAP]
+ * (-1 padded), int16 lidx[128][27] (-1 = absent).  ucount > UCAP marks a tile whose neighbourhood does not fit (its uniq /
+ * lidx are not written; consumers read nbr directly for it).  plan: >= cdseg_conv_plan_bytes(n) bytes, 16-byte aligned. */
+#define CDSEG_CONV_PLAN_UCAP 384
+size_t cdseg_conv_plan_bytes(int64_t n);
+int cdseg_conv_tile_plan(const int32_t* nbr, int64_t n, void* plan, void* stream);
 /* which fused kernels cdseg_block_forward uses: bit 0 post-attention chain, bit 1 pre-attention chain (default: all) */
 void cdseg_set_fused_mask(int mask);
 
@@ -164,6 +173,7 @@ typedef struct CdsegBlockArgs {
   int64_t n; int C, H, T_dim, B;                 /* points, channels, heads (C = 16 H), timestep width, scenes */
   const float* x; const float* conv_in;           /* block input; conv_in != NULL: tensor the CPE conv reads (stale-feature quirk) */
   const int32_t* nbr; const uint32_t* tile_mask; const int32_t* batch;
+  const void* conv_plan;                          /* cdseg_conv_tile_plan(nbr) or NULL (then the unfused conv path runs) */
   const float* t_scene;                           /* [B, T_dim] per-scene timestep features or NULL (CN blocks) */
   const int32_t* slot_src; const int32_t* slot_dst; const int32_t* patch_len; int T, Kp; float scale;
   const float* conv_Bp; const float* conv_b;      /* packed operands come from cdseg_gemm_pack_b */

@@ -61,6 +61,9 @@ order, _ = ops.argsort_rows(codes, 27)
 grid = grid[order[0].long()].contiguous()
 nbr = ops.nbr_build(grid, batch, 3)
 mask = ops.tile_tap_mask(nbr)
+plan = ops.conv_tile_plan(nbr)
+U = plan.view(-1, plan.numel() // ((n + 127) // 128))[:, :4].contiguous().view(torch.int32).flatten()
+print(f"conv tile plan: {U.numel()} tiles, distinct neighbour rows per tile mean {U.float().mean().item():.1f} max {U.max().item()} (cache {ops.CONV_PLAN_UCAP})")
 for C in (32, 64):
     x = torch.randn(n, C, device=dev)
     wc = torch.randn(27, C, C, device=dev) / (27 * C * 0.4) ** 0.5
@@ -76,7 +79,7 @@ for C in (32, 64):
         return x1, ops.gemm_tc(h, qk[0], 3 * C, C, bias=qk[1])
 
     def new():
-        return ops.pre_attn(x, x, nbr, mask, conv, l1, (cg, cb), (g1, b1), qk)
+        return ops.pre_attn(x, x, nbr, mask, plan, conv, l1, (cg, cb), (g1, b1), qk)
     (a1, aq), (b1_, bq) = old(), new()
     err = max((a1 - b1_).abs().max().item(), (aq - bq).abs().max().item())
     for cold in (False, True):

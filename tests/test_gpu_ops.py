@@ -383,14 +383,53 @@ def test_post_attn_chain_vs_fp64(ops, n, C):
     assert err < 3e-5 * max(1.0, ref.abs().max().item()), err
 
 
+def _curve_sorted(sc):
+    """the scene's points renumbered along the z curve (what structure.Plan does to every level): neighbours of a 128-row tile
+    are then few distinct rows"""
+    g, b = sc["grid_coord"], S.offset2batch(sc["offset"])
+    code, order, _, _ = S.serialization(g, b)
+    return np.ascontiguousarray(g[order[0]]), np.ascontiguousarray(b[order[0]])
+
+
+@pytest.mark.parametrize("counts,curve", [((1500, 600), True), ((1500, 600), False), ((130,), True), ((9000,), True)])
+def test_conv_tile_plan_bit_exact(ops, counts, curve):
+    """per 128-row tile: ascending distinct neighbour rows + local index of every (row, tap) (include/cdseg_b200.h)"""
+    sc = _scene(counts)
+    g, b = _curve_sorted(sc) if curve else (sc["grid_coord"], S.offset2batch(sc["offset"]))
+    nbr = ops.nbr_build(cu(g), cu(b, torch.int32), 3)
+    plan = ops.conv_tile_plan(nbr).cpu().numpy()
+    nb = nbr.cpu().numpy()
+    UCAP = ops.CONV_PLAN_UCAP
+    rec = 16 + 4 * UCAP + 128 * 27 * 2
+    assert plan.size == -(-len(nb) // 128) * rec
+    cached = 0
+    for t in range(-(-len(nb) // 128)):
+        r = plan[t * rec:(t + 1) * rec]
+        rows = nb[t * 128:(t + 1) * 128]
+        uniq = np.unique(rows[rows >= 0])
+        assert int(r[:4].view(np.int32)[0]) == len(uniq)
+        if len(uniq) > UCAP:
+            continue
+        cached += 1
+        u = r[16:16 + 4 * UCAP].view(np.int32)
+        assert np.array_equal(u[:len(uniq)], uniq) and np.all(u[len(uniq):] == -1)
+        li = r[16 + 4 * UCAP:].view(np.int16).reshape(128, 27)[:len(rows)]
+        exp = np.where(rows >= 0, np.searchsorted(uniq, np.maximum(rows, 0)), -1)
+        assert np.array_equal(li, exp)
+    assert cached > 0 or not curve
+
+
 @pytest.mark.timeout(180)
+@pytest.mark.parametrize("curve", (True, False))
 @pytest.mark.parametrize("counts,C,with_t,stale", [((1500, 600), 32, False, False), ((1500, 600), 32, True, True), ((3000,), 64, True, False),
                                                     ((900, 500), 128, False, True), ((130,), 64, False, False)])
-def test_pre_attn_chain_vs_fp64(ops, counts, C, with_t, stale):
+def test_pre_attn_chain_vs_fp64(ops, counts, C, with_t, stale, curve):
     """cpe conv + Linear + LayerNorm + residual (+ per-scene t) + norm1 + qkv in ONE kernel == the fp64 composition
-    (ptv3.py:355-362, 400-413, 258); `stale` = the conv reads another tensor than the residual (unpooling quirk)"""
+    (ptv3.py:355-362, 400-413, 258); `stale` = the conv reads another tensor than the residual (unpooling quirk);
+    `curve` = rows numbered along the z curve (tiles use the shared-memory neighbour cache) or in generation order
+    (neighbourhoods too scattered for the cache: the direct-gather fallback)"""
     sc = _scene(counts)
-    g, b = sc["grid_coord"], S.offset2batch(sc["offset"])
+    g, b = _curve_sorted(sc) if curve else (sc["grid_coord"], S.offset2batch(sc["offset"]))
     n = len(g)
     gen = torch.Generator().manual_seed(C + n)
     x = torch.randn(n, C, generator=gen)
@@ -410,7 +449,7 @@ def test_pre_attn_chain_vs_fp64(ops, counts, C, with_t, stale):
     mask = ops.tile_tap_mask(nbr)
     pk = lambda w, bb: (ops.gemm_pack_b(w.t().contiguous()[None].to(DEV)), bb.to(DEV))
     conv = (ops.gemm_pack_b(wc.reshape(C, 27, C).permute(1, 2, 0).contiguous().to(DEV)), bc.to(DEV))
-    o1, oq = ops.pre_attn(cin.to(DEV), x.to(DEV), nbr, mask, conv, pk(wl, bl), (cg.to(DEV), cb.to(DEV)), (g1.to(DEV), b1.to(DEV)),
+    o1, oq = ops.pre_attn(cin.to(DEV), x.to(DEV), nbr, mask, ops.conv_tile_plan(nbr), conv, pk(wl, bl), (cg.to(DEV), cb.to(DEV)), (g1.to(DEV), b1.to(DEV)),
                           pk(wq, bq), tproj.to(DEV) if with_t else None, cu(b, torch.int32) if with_t else None, 1e-5)
     torch.cuda.synchronize()
     e1 = (o1.cpu().double() - x1).abs().max().item()
