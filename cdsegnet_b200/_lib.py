@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
-SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu"]
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "losses.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
@@ -123,6 +123,11 @@ SIGNATURES = {
     "cdseg_event_destroy": (None, [_P]),
     "cdseg_event_elapsed_ms": (_I, [_P, _P, ctypes.POINTER(_F)]),
     "cdseg_conv_im2col_tc": (_I, [_P, _P, _I, _P, _L, _I, _P, _I, _P, _L, _P]),
+    "cdseg_criteria_workspace_bytes": (_Z, [_L, _I]),
+    "cdseg_criteria": (_I, [_P, _P, _L, _I, _L, _P, _P, _I, _I, _F, _F, _F, _I, _I, _I, _P, _P, _Z, _P]),
+    "cdseg_q_sample": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P]),
+    "cdseg_ddim_step": (_I, [_P, _P, _L, _F, _F, _F, _F, _I, _I, _P, _P]),
+    "cdseg_axpy_scale": (_I, [_P, _P, _F, _F, _L, _P]),
     "cdseg_gemm_tc": (_I, [_P, _L, _P, _I, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P, _L, _I, _P, _Z, _P]),
 }
 

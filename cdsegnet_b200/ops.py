@@ -372,3 +372,45 @@ def gemm_tc(A, Bp, N, K, idx=None, tile_mask=None, bias=None, res=None, act=0, n
                             _p(bias), _p(res), res.shape[1] if res is not None else 0, act, _p(out), N, nsplit, _p(ws), nb,
                             _stream()), "gemm_tc")
     return out
+
+
+# ---------------------------------------------------------------- wrapper: criteria + diffusion samplers (losses.cu)
+def criteria(n_pred, n_target, ignore_index=-1, c_pred=None, c_target=None, mse_use_ignore=True, weights=(1.0, 1.0, 1.0),
+             has=(True, True, True)):
+    """forward values of MSE / CE / Lovasz and their EW / GLS combinations -> fp32 [5] on the device
+    ([0] MSE, [1] CE, [2] Lovasz, [3] sum, [4] sqrt(MSE * (CE + Lovasz))); see include/cdseg_b200.h"""
+    lib = _lib.load()
+    n, C = n_pred.shape
+    has_mse = bool(has[0]) and c_pred is not None and c_target is not None
+    out = torch.empty(5, dtype=torch.float32, device=n_pred.device)
+    nb = lib.cdseg_criteria_workspace_bytes(n, C)
+    ws = _ws(nb, n_pred.device)
+    check(lib.cdseg_criteria(_p(n_pred, torch.float32), _p(n_target, torch.int64), n, C, int(ignore_index),
+                             _p(c_pred, torch.float32) if has_mse else None, _p(c_target, torch.float32) if has_mse else None,
+                             c_pred.shape[1] if has_mse else 0, int(bool(mse_use_ignore)), float(weights[0]), float(weights[1]),
+                             float(weights[2]), int(has_mse), int(bool(has[1])), int(bool(has[2])), _p(out), _p(ws), nb, _stream()),
+          "criteria")
+    return out
+
+
+def q_sample(x0, noise, batch, sqrt_ab, sqrt_1mab):
+    """x_t = sqrt_ab[batch] * x0 + sqrt_1mab[batch] * noise (default.py:216-222); sqrt_* fp32 [B] on the device"""
+    out = torch.empty_like(x0)
+    n, C = x0.shape
+    check(_lib.load().cdseg_q_sample(_p(x0, torch.float32), _p(noise, torch.float32), _p(batch, torch.int32), _p(sqrt_ab, torch.float32),
+                                     _p(sqrt_1mab, torch.float32), n, C, _p(out), _stream()), "q_sample")
+    return out
+
+
+def ddim_step(x_t, pred, sqrt_ab, sqrt_1mab, sqrt_ab_prev, sqrt_1mab_prev, target_is_x0, last):
+    out = torch.empty_like(x_t)
+    check(_lib.load().cdseg_ddim_step(_p(x_t, torch.float32), _p(pred, torch.float32), x_t.numel(), float(sqrt_ab), float(sqrt_1mab),
+                                      float(sqrt_ab_prev), float(sqrt_1mab_prev), int(target_is_x0), int(last), _p(out), _stream()),
+          "ddim_step")
+    return out
+
+
+def axpy_scale_(y, x, a=1.0, scale=1.0):
+    check(_lib.load().cdseg_axpy_scale(_p(y, torch.float32), _p(x, torch.float32), float(a), float(scale), y.numel(), _stream()),
+          "axpy_scale")
+    return y

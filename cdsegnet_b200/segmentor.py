@@ -1,10 +1,18 @@
 """``DefaultSegmentorV2`` (CNF, variant (1)) boundary: pointcept/models/default.py:13-494.
 
-Implements the single-step inference (SSI) path ``inference(input_dict, eval, noise_level)``
-(default.py:371-422) on top of the B200 backbone, with the reference's RNG coupling kept
-(the N(0,1) draw for the Noise-Network input comes from torch's CPU generator exactly like
-default.py:393) but with the timestep embedding built once per SCENE instead of per point.
-``forward`` (training loss) and ``inference_ddim`` are the next §8(f) rows.
+Same constructor kwargs, same methods and return dicts as the reference wrapper:
+  inference(input_dict, eval, noise_level)            single-step inference (SSI), default.py:371-422
+  inference_ddim(input_dict, T, step, report, eval, mode, noise_level)   multi-step DDIM inference, default.py:278-369
+  forward(input_dict)                                 criteria of the training pass, default.py:424-493 (values only)
+plus the diffusion schedule (get_diffusion_hyperparams / get_diffusion_betas, default.py:75-189), the samplers
+(continuous_q_sample / continuous_p_ddim_sample, 192-222) and the input-noise helpers (228-269).
+
+The reference's RNG coupling is kept: the N(0,1) draw of the Noise-Network input, the training timesteps and the
+training noise come from torch's CPU generator in the reference's order (`torch.normal(...).cuda()`, default.py:393,
+455, 462), so a seeded run reproduces the reference's draws.  Differences, on purpose: the timestep embedding is built
+once per SCENE instead of per point (identical rows), the criteria run as one fused device call
+(cdsegnet_b200/losses.py) and there is no backward pass yet: `forward` refuses to run in train mode instead of
+returning a loss nobody can differentiate.
 """
 import math
 
@@ -12,6 +20,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import ops
+from .losses import build_criteria
 from .registry import build_model
 
 
@@ -30,26 +40,129 @@ class DefaultSegmentorV2(nn.Module):
                  dm_target="noise", dm_min_snr=None, condition=False, c_in_channels=6):
         super().__init__()
         self.backbone = build_model(backbone) if isinstance(backbone, dict) else backbone
-        self.criteria_cfg = criteria            # losses are stock torch; not on the inference hot path
+        self.criteria = build_criteria(cfg=criteria, loss_type=loss_type, task_num=task_num)
         self.num_classes, self.T, self.T_dim = num_classes, T, T_dim
+        self.beta_start, self.beta_end, self.noise_schedule = beta_start, beta_end, noise_schedule
         self.condition, self.dm, self.dm_input, self.dm_target = condition, dm, dm_input, dm_target
+        self.dm_min_snr = dm_min_snr
         self.c_in_channels = c_in_channels
+        self._dev_sched = {}
+        if self.dm:
+            self.eps = 1e-6
+            Beta, Alpha, Alpha_bar, Sigma, SNR = self.get_diffusion_hyperparams(noise_schedule=noise_schedule, T=T,
+                                                                                beta_start=beta_start, beta_end=beta_end)
+            # the reference moves these to the GPU here (default.py:68-72); they are 5 x T floats, kept on the host and
+            # mirrored per device on first use
+            self.Beta, self.Alpha, self.Alpha_bar, self.Sigma = Beta.float(), Alpha.float(), Alpha_bar.float(), Sigma.float()
+            self.SNR = SNR.float() if dm_min_snr is None else torch.clamp(SNR.float(), max=dm_min_snr)
 
+    # ------------------------------------------------------------------------------------------ schedule
+    def get_diffusion_betas(self, type="linear", start=0.0001, stop=0.02, T=1000):
+        """default.py:127-189, fp64"""
+        lin = lambda a, b, n: torch.linspace(a, b, n, dtype=torch.float64)
+        if type == "linear":
+            return lin(1000 / T * start, 1000 / T * stop, T)
+        if type == "cosine":
+            u = lin(start, stop, T + 1) / T                     # sic: the reference spans [start, stop] / T (default.py:145)
+            cum = torch.cos((u + 0.008) / 1.008 * math.pi * 0.5) ** 2
+        elif type == "sigmoid":
+            u = lin(0, T, T + 1) / T
+            s0, s1 = torch.tensor(-3.0).sigmoid(), torch.tensor(3.0).sigmoid()
+            cum = (-(u * 6 - 3).sigmoid() + s1) / (s1 - s0)
+        else:
+            raise NotImplementedError(type)                     # "laplace" fails inside the reference as well (default.py:184)
+        cum = cum / cum[0]
+        return torch.clip(1 - cum[1:] / cum[:-1], 0, 0.999)
+
+    def get_diffusion_hyperparams(self, noise_schedule, beta_start, beta_end, T):
+        """default.py:75-125 -> Beta, Alpha, Alpha_bar, Sigma, SNR (fp64 [T])"""
+        Beta = self.get_diffusion_betas(type=noise_schedule, start=beta_start, stop=beta_end, T=T)
+        Alpha = 1 - Beta
+        Alpha_bar = torch.cumprod(Alpha, 0)
+        prev = torch.cat([Alpha_bar.new_zeros(1), Alpha_bar[:-1]])
+        var = Beta * ((1 - prev) / (1 - Alpha_bar))
+        var[0] = Beta[0]
+        Sigma = torch.sqrt(var)
+        Sigma[0] = 0.0
+        return Beta, Alpha, Alpha_bar, Sigma, Alpha_bar / (1 - Alpha_bar)
+
+    def get_time_schedule(self, T=1000, step=5):
+        return np.linspace(-1, T - 1, num=step + 1, dtype=int)[::-1]
+
+    def _sched(self, dev):
+        """(sqrt(Alpha_bar), sqrt(1 - Alpha_bar)) as fp32: host copies for scalar lookups + device copies for gathers"""
+        if dev not in self._dev_sched:
+            sa, sb = torch.sqrt(self.Alpha_bar), torch.sqrt(1 - self.Alpha_bar)
+            self._dev_sched[dev] = (sa, sb, sa.to(dev), sb.to(dev))
+        return self._dev_sched[dev]
+
+    def continuous_q_sample(self, x_0, t, noise=None):
+        """x_t = sqrt(Alpha_bar[t]) x_0 + sqrt(1 - Alpha_bar[t]) noise; t int64 [N,1] (one timestep per row), default.py:216-222"""
+        if noise is None:
+            noise = torch.normal(0, 1, size=x_0.shape, dtype=torch.float32).to(x_0.device)
+        _, _, sa, sb = self._sched(x_0.device)
+        rows = torch.arange(x_0.shape[0], dtype=torch.int32, device=x_0.device)
+        tt = t.view(-1).to(x_0.device)
+        return ops.q_sample(x_0.float().contiguous(), noise.float().contiguous(), rows, sa[tt].contiguous(), sb[tt].contiguous())
+
+    def continuous_p_ddim_sample(self, x_t, t, noise):
+        """default.py:192-214.  t: int64 [N,1] with one value for all rows (what inference_ddim passes) or a python int;
+        negative values index the schedule from its end like the reference's tensor indexing."""
+        tv = int(t.view(-1)[0]) if torch.is_tensor(t) else int(t)
+        sa, sb, _, _ = self._sched(x_t.device)
+        return ops.ddim_step(x_t.float().contiguous(), noise.float().contiguous(), float(sa[tv]), float(sb[tv]), float(sa[tv - 1]),
+                             float(sb[tv - 1]), self.dm_target == "x0", tv == 0)
+
+    # ------------------------------------------------------------------------------------------ input noise helpers
+    def add_gaussian_noise(self, pts, sigma=0.1, clamp=0.03):
+        assert clamp > 0
+        return sigma * torch.randn_like(pts) + pts
+
+    def add_random_noise(self, pts, sigma=0.1, clamp=0.03):
+        assert clamp > 0
+        return sigma * torch.rand_like(pts) + pts
+
+    def add_laplace_noise(self, pts, sigma=0.1, clamp=0.03, loc=0.0, scale=1.0):
+        assert clamp > 0
+        return sigma * torch.distributions.Laplace(loc=loc, scale=scale).sample(pts.shape).to(pts.device) + pts
+
+    def add_possion_noise(self, pts, sigma=0.1, clamp=0.03, rate=3.0):
+        assert clamp > 0
+        return sigma * torch.distributions.Poisson(rate).sample(pts.shape).to(pts.device) + pts
+
+    def init_feature(self, input_dict):
+        return dict(coord=input_dict["coord"], grid_coord=input_dict["grid_coord"], offset=input_dict["offset"])
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _c_target(self, input_dict):
+        feat = input_dict["feat"]
+        return feat if self.c_in_channels == feat.shape[-1] else input_dict["coord"]
+
+    def _t_emb(self, t, input_dict):
+        """one row per scene (the reference builds N identical rows per scene, default.py:400-403)"""
+        B = input_dict["offset"].numel()
+        ts = t * torch.ones((B, 1), dtype=torch.int64, device=input_dict["feat"].device)
+        return calc_t_emb(ts, self.T_dim)
+
+    def _result(self, logits, input_dict, eval):
+        if not eval:
+            return dict(seg_logits=logits)
+        loss = self.criteria(dict(n_pred=logits, n_target=input_dict["segment"], loss_mode="eval"))
+        return dict(loss=loss, seg_logits=logits)
+
+    # ------------------------------------------------------------------------------------------ inference
     @torch.no_grad()
     def inference(self, input_dict, eval=True, noise_level=None, noise=None):
-        """-> dict(seg_logits=[N, num_classes]).  `noise` optionally injects the NN input
+        """-> dict(seg_logits=[N, num_classes]) (+ loss when eval).  `noise` optionally injects the Noise-Network input
         (otherwise drawn like default.py:393: CPU generator, then moved to the GPU)."""
-        if eval:
-            raise NotImplementedError("eval=True (loss on the validation pass) needs the criteria; "
-                                      "use eval=False as tools/test_CDSegNet_*.py do (engines/test.py:214-218)")
+        if noise_level is not None:
+            input_dict = dict(input_dict, feat=self.add_gaussian_noise(input_dict["feat"], sigma=noise_level))
         feat = input_dict["feat"]
-        if noise_level is not None:              # add_gaussian_noise, default.py:225-233
-            feat = feat + noise_level * torch.randn_like(feat)
-        base = dict(coord=input_dict["coord"], grid_coord=input_dict["grid_coord"], offset=input_dict["offset"])
+        base = self.init_feature(input_dict)
         if not self.condition:
             n_point = self.backbone(n_point=dict(base, feat=feat))
-            return dict(seg_logits=n_point["feat"])
-        c_target = feat if self.c_in_channels == feat.shape[-1] else input_dict["coord"]
+            return self._result(n_point["feat"], input_dict, eval)
+        c_target = self._c_target(input_dict)
         c_feat, t = c_target, 0
         if self.dm and self.dm_input == "xt":
             if noise is None:
@@ -58,8 +171,77 @@ class DefaultSegmentorV2(nn.Module):
             t = self.T - 1
         c_point = dict(base, feat=c_feat)
         if self.T_dim != -1:
-            B = input_dict["offset"].numel()
-            ts = t * torch.ones((B, 1), dtype=torch.int64, device=feat.device)
-            c_point["t_emb"] = calc_t_emb(ts, self.T_dim)          # one row per scene
+            c_point["t_emb"] = self._t_emb(t, input_dict)
         c_point, n_point = self.backbone(c_point, dict(base, feat=feat))
-        return dict(seg_logits=n_point["feat"])
+        return self._result(n_point["feat"], input_dict, eval)
+
+    @torch.no_grad()
+    def inference_ddim(self, input_dict, T=1000, step=1, report=10, eval=True, mode="avg", noise_level=None):
+        """multi-step DDIM inference, default.py:278-369: `step` + 1 backbone passes over the time schedule (the last one
+        at t = -1, which indexes the schedule from its end -- a reference quirk kept for parity), the Noise-Network input
+        updated by the DDIM rule after every pass, logits averaged ("avg") or taken from the last pass ("final")."""
+        if noise_level is not None:
+            input_dict = dict(input_dict, feat=self.add_gaussian_noise(input_dict["feat"], sigma=noise_level))
+        feat = input_dict["feat"]
+        base = self.init_feature(input_dict)
+        if not self.condition:
+            n_point = self.backbone(n_point=dict(base, feat=feat))
+            return self._result(n_point["feat"], input_dict, eval)
+        c_target = self._c_target(input_dict)
+        c_xt = torch.normal(0, 1, size=c_target.shape, dtype=torch.float32).to(feat.device)
+        n_pred = torch.zeros((len(c_target), self.num_classes), dtype=torch.float32, device=feat.device)
+        time_schedule = self.get_time_schedule(T, step)
+        for i, t in zip(reversed(range(len(time_schedule))), time_schedule):
+            t = int(t)
+            if (i + 1) % report == 0 or t <= 0:
+                print(f"  ---- current : [{i + 1 if t > 0 else 0}/{step}] steps ----")
+            c_point = dict(base, feat=c_xt)
+            if self.T_dim != -1:
+                c_point["t_emb"] = self._t_emb(t, input_dict)
+            c_point, n_point = self.backbone(c_point, dict(base, feat=feat))
+            c_xt = self.continuous_p_ddim_sample(c_xt, t, c_point["feat"])
+            if mode == "avg":
+                ops.axpy_scale_(n_pred, n_point["feat"])
+            elif mode == "final":
+                n_pred = n_point["feat"]
+            if t <= 0:
+                break
+        if mode == "avg":
+            ops.axpy_scale_(n_pred, n_pred, a=0.0, scale=1.0 / len(time_schedule))
+        return self._result(n_pred, input_dict, eval)
+
+    # ------------------------------------------------------------------------------------------ training criteria
+    @torch.no_grad()
+    def forward(self, input_dict):
+        """-> dict(loss=...) of the training pass (default.py:424-493): random timestep per scene, q-sampled Noise-Network
+        input, criteria in "train" mode (GLS).  Values only -- no autograd graph is built, and the backbone evaluates its
+        BatchNorms with running statistics; training needs the backward kernels of the §8(f) row."""
+        if self.training:
+            raise NotImplementedError("cdsegnet_b200 has no backward pass yet: call .eval() to evaluate the training criteria, "
+                                      "or train with the reference and load the checkpoint here")
+        feat = input_dict["feat"]
+        base = self.init_feature(input_dict)
+        point = {}
+        if self.condition:
+            c_target = self._c_target(input_dict)
+            c_point = dict(base, feat=c_target)
+            if self.dm:
+                offset = input_dict["offset"]
+                B = offset.numel()                                   # == len(torch.unique(batch)) for non-empty scenes
+                ts = torch.randint(0, self.T, size=(B, 1), dtype=torch.int64)
+                if self.T_dim != -1:
+                    c_point["t_emb"] = calc_t_emb(ts.to(feat.device), self.T_dim)
+                c_noise = torch.normal(0, 1, size=c_target.shape, dtype=torch.float32).to(feat.device)
+                _, _, sa, sb = self._sched(feat.device)
+                tt = ts.view(-1).to(feat.device)
+                batch = ops.offset2batch(offset.long().contiguous(), c_target.shape[0])
+                c_point["feat"] = ops.q_sample(c_target.float().contiguous(), c_noise, batch, sa[tt].contiguous(), sb[tt].contiguous())
+                if self.dm_target == "noise":
+                    c_target = c_noise
+                # (SNR loss weights, default.py:471-473, never reach MSELoss: misc.py:84 tests hasattr() on a dict)
+            c_point, n_point = self.backbone(c_point, dict(base, feat=feat))
+            point["c_pred"], point["c_target"] = c_point["feat"], c_target
+        else:
+            n_point = self.backbone(n_point=dict(base, feat=feat))
+        point["n_pred"], point["n_target"], point["loss_mode"] = n_point["feat"], input_dict["segment"], "train"
+        return dict(loss=self.criteria(point))

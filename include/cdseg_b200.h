@@ -192,6 +192,27 @@ void* cdseg_event_create(void);
 void cdseg_event_destroy(void* e);
 int cdseg_event_elapsed_ms(void* e0, void* e1, float* ms);
 
+/* ---- DefaultSegmentorV2 wrapper: criteria (forward values) and diffusion samplers ------------------------------------
+ * Criteria of pointcept/models/losses/builder.py:14-51 over MSELoss (misc.py:24-94, batch_sample_point <= 0),
+ * CrossEntropyLoss (misc.py:97-129) and LovaszLoss mode="multiclass" (lovasz.py:118-165, 244-272), all with one shared
+ * ignore_index.  n_pred fp32 [n, C] logits, n_target int64 [n]; c_pred / c_target fp32 [n, Cc] (Noise-Network output and
+ * its diffusion target) or NULL with has_mse = 0.  out5 (device, fp32): [0] MSE, [1] CE, [2] Lovasz (mean over the classes
+ * present among the valid labels), [3] their sum (loss_type "EW" and every eval pass), [4] sqrt(MSE * (CE + Lovasz))
+ * (loss_type "GLS", task_num = 2, training pass).  Caller allocates the workspace; nothing is copied to the host. */
+size_t cdseg_criteria_workspace_bytes(int64_t n, int C);
+int cdseg_criteria(const float* n_pred, const int64_t* n_target, int64_t n, int C, int64_t ignore_index, const float* c_pred,
+                   const float* c_target, int Cc, int mse_use_ignore, float w_mse, float w_ce, float w_lov, int has_mse,
+                   int has_ce, int has_lov, float* out5, void* workspace, size_t workspace_bytes, void* stream);
+/* continuous_q_sample, default.py:216-222: out = sqrt_ab[b] * x0 + sqrt_1mab[b] * noise, b = batch[row] (batch NULL: b = 0) */
+int cdseg_q_sample(const float* x0, const float* noise, const int32_t* batch, const float* sqrt_ab, const float* sqrt_1mab,
+                   int64_t n, int C, float* out, void* stream);
+/* continuous_p_ddim_sample, default.py:192-214, one timestep shared by all rows: the four scalars are sqrt(Alpha_bar[t]),
+ * sqrt(1 - Alpha_bar[t]) and the same at t - 1; last != 0 returns the x0 estimate (t == 0) */
+int cdseg_ddim_step(const float* x_t, const float* pred, int64_t total, float sqrt_ab, float sqrt_1mab, float sqrt_ab_prev,
+                    float sqrt_1mab_prev, int target_is_x0, int last, float* out, void* stream);
+/* y = (y + a * x) * scale  (the "avg" accumulation of inference_ddim, default.py:342, 359) */
+int cdseg_axpy_scale(float* y, const float* x, float a, float scale, int64_t total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
