@@ -225,11 +225,18 @@ def run_cuda(args):
     e2e = world * n * args.steps / (ms_e2e / 1e3)
     hbm, tf_burst, tf_sust, which = peaks()
 
-    # Per-kernel numbers, measured live with CUDA events on the launching stream inside the timed steps above.
-    #  * dominant kernel by device time = gt::gemm_tc_kernel (profiles/): a skinny, HBM-bound GEMM.  Representative launch:
-    #    the stage-0 MLP fc1 (120k x 32 -> 128, bias + GELU fused).  Algorithmic bytes = read A (n*C*4) + write out
-    #    (n*4C*4) + packed weights (read once).
+    # Per-kernel numbers, measured live with CUDA events on the launching stream inside the timed steps above (the events are
+    # recorded by cdseg_block_forward around its own launches).
+    #  * dominant launch configuration by device time (profiles/r01d_launches_step_v4.md) = fz::pre_kernel at stage 0: the fused
+    #    cpe conv + Linear + LayerNorm + residual + norm1 + qkv chain, 12 launches/step.  Its roofline is HBM: algorithmic bytes =
+    #    read the block input once (n*C*4; conv operand and residual are the same tensor) + the neighbour table (n*27*4) +
+    #    write x1 (n*C*4) and qkv (n*3C*4) + the packed weights once.  The tensor-pipe view of the same launch is reported next
+    #    to it (FLOPs = 2 * (conv pairs + 4n) * C^2, x3 MMAs for the fp16 hi/lo split are NOT counted).
     #  * the one dense contraction north_star names = tc2::attn_tc2_kernel at stage 0 (tensor/MUFU bound).
+    #  * `traffic` = dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+    #    (profiles/r01d_ncu_*.md, same workload, same launch).
+    NCU_TRAFFIC = {"pre": 23.377152e6 + 5.710592e6, "attn": 31.441664e6 + 0.014848e6}
+
     def kernel_lines(prof, steps):
         lib = ops._lib.load()
         import ctypes
@@ -241,26 +248,39 @@ def run_cuda(args):
         nmax = max(p["n"] for p in prof)
         sel = [p for p in prof if p["n"] == nmax and p["C"] == 32]
         t_attn = sum(ms(p["ev"][0], p["ev"][1]) for p in sel) / len(sel)
-        t_fc1 = sum(ms(p["ev"][2], p["ev"][3]) for p in sel) / len(sel)
+        t_post = sum(ms(p["ev"][2], p["ev"][3]) for p in sel) / len(sel)
+        t_pre = sum(ms(p["ev"][4], p["ev"][5]) for p in sel) / len(sel)
         p0 = sel[0]
-        fl = 4.0 * p0["pairs"] * p0["C"]
+        n0, C0 = p0["n"], p0["C"]
+        fl = 4.0 * p0["pairs"] * C0
         ex = p0["pairs"] * p0["H"]
         attn = {"bound": "tensor", "kernel": "tc2::attn_tc2_kernel (stage 0, %d launches/step)" % (len(sel) // steps),
                 "achieved": fl / (t_attn * 1e-3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s", "frac": fl / (t_attn * 1e-3) / 1e12 / tf_sust,
                 "flops_per_launch": fl, "ms_per_launch": t_attn, "exp_per_launch": ex, "gexp_per_s": ex / (t_attn * 1e-3) / 1e9,
-                "mufu_peak_gexp_per_s": 148 * 16 * 1.965, "traffic": None}
-        by = p0["n"] * p0["C"] * 4 + p0["n"] * 4 * p0["C"] * 4 + 2 * 4 * p0["C"] * p0["C"] * 2
-        roof = {"bound": "hbm", "kernel": "gt::gemm_tc_kernel (stage-0 MLP fc1 120000x32->128 + GELU, %d launches/step)" % (len(sel) // steps),
-                "achieved": by / (t_fc1 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / (t_fc1 * 1e-3) / 1e9 / hbm,
-                "peak_source": which, "bytes_per_launch": by, "ms_per_launch": t_fc1, "traffic": None}
+                "mufu_peak_gexp_per_s": 148 * 16 * 1.965, "traffic": NCU_TRAFFIC["attn"]}
+        wbytes = (27 + 1 + 3) * C0 * C0 * 4
+        by = n0 * C0 * 4 + n0 * 27 * 4 + n0 * C0 * 4 + n0 * 3 * C0 * 4 + wbytes
+        pre_fl = 2.0 * (conv_pairs + 4 * n0) * C0 * C0
+        roof = {"bound": "hbm", "kernel": "fz::pre_kernel (stage 0: cpe conv + Linear + LN + residual + norm1 + qkv fused, n=%d C=%d, %d launches/step)"
+                % (n0, C0, len(sel) // steps),
+                "achieved": by / (t_pre * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / (t_pre * 1e-3) / 1e9 / hbm,
+                "peak_source": which, "bytes_per_launch": by, "ms_per_launch": t_pre, "traffic": NCU_TRAFFIC["pre"],
+                "tensor_view": {"flops_per_launch": pre_fl, "achieved_tflops": pre_fl / (t_pre * 1e-3) / 1e12,
+                                "frac_of_bf16_peak": pre_fl / (t_pre * 1e-3) / 1e12 / tf_sust}}
+        pby = 3 * n0 * C0 * 4 + 9 * C0 * C0 * 4
+        post = {"bound": "hbm", "kernel": "fz::post_kernel (stage 0: proj + residual + norm2 + fc1 + GELU + fc2 + residual fused)",
+                "achieved": pby / (t_post * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": pby / (t_post * 1e-3) / 1e9 / hbm,
+                "bytes_per_launch": pby, "ms_per_launch": t_post, "traffic": None}
         for p in prof:
             for e in p["ev"]:
                 lib.cdseg_event_destroy(e)
-        return roof, attn
+        return roof, attn, post
 
-    roof = attn = None
+    roof = attn = post = None
     if prof:
-        roof, attn = kernel_lines(prof, args.steps)
+        nb3 = seg.backbone.last_plan.n_levels[0].nbr(3)
+        conv_pairs = int((nb3 >= 0).sum().item())                      # (active output, active input) pairs of the k=3 conv at level 0
+        roof, attn, post = kernel_lines(prof, args.steps)
         # In the timed region above the Noise Network runs on a second stream beside the Conditional Network, so the
         # events around one launch also cover whatever the other stream had resident.  A few extra steps with the
         # two-stream schedule switched off give the same launches alone on the device (reported next to the in-step time).
@@ -268,8 +288,8 @@ def run_cuda(args):
         k1 = max(2, min(5, args.steps))
         _, _, _, prof1 = timed(step_resident, k1, 1, profile_attn=True)
         seg.backbone.overlap_streams = True
-        r1, a1 = kernel_lines(prof1, k1)
-        for full, alone in ((roof, r1), (attn, a1)):
+        r1, a1, p1 = kernel_lines(prof1, k1)
+        for full, alone in ((roof, r1), (attn, a1), (post, p1)):
             full["single_stream"] = {"ms_per_launch": alone["ms_per_launch"], "achieved": alone["achieved"], "frac": alone["frac"]}
 
     line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -284,7 +304,7 @@ def run_cuda(args):
             "e2e": {"value": e2e, "unit": "points/s",
                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) + n * 6 * 4),
                     "d2h_bytes_per_step": int(n * 20 * 4), "ms_per_step": ms_e2e / args.steps},
-            "roofline": roof, "roofline_attention": attn}
+            "roofline": roof, "roofline_attention": attn, "roofline_post": post}
     if rank == 0:
         if world == 1 and not args.no_cpu:
             v, cores, dt = cpu_forward_timed(args.cpu_points)

@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
-SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "losses.cu"]
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "losses.cu", "fragments.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
@@ -72,7 +72,7 @@ class BlockArgs(ctypes.Structure):
                 ("conv_Bp", _P), ("conv_b", _P), ("lin_Bp", _P), ("lin_b", _P), ("cpe_g", _P), ("cpe_b", _P),
                 ("t_W", _P), ("t_b", _P), ("n1_g", _P), ("n1_b", _P), ("qkv_Bp", _P), ("qkv_b", _P), ("proj_Bp", _P),
                 ("proj_b", _P), ("n2_g", _P), ("n2_b", _P), ("fc1_Bp", _P), ("fc1_b", _P), ("fc2_Bp", _P), ("fc2_b", _P),
-                ("ln_eps", _F), ("out", _P), ("scratch", _P), ("scratch_bytes", _Z), ("ev", _P * 4)]
+                ("ln_eps", _F), ("out", _P), ("scratch", _P), ("scratch_bytes", _Z), ("ev", _P * 6)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/cdseg_b200.h
@@ -128,6 +128,11 @@ SIGNATURES = {
     "cdseg_q_sample": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P]),
     "cdseg_ddim_step": (_I, [_P, _P, _L, _F, _F, _F, _F, _I, _I, _P, _P]),
     "cdseg_axpy_scale": (_I, [_P, _P, _F, _F, _L, _P]),
+    "cdseg_grid_sample_workspace_bytes": (_Z, [_L]),
+    "cdseg_grid_sample_plan": (_I, [_P, _I, _L, ctypes.c_double, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "cdseg_fragment_index": (_I, [_P, _P, _I, _I, _P, _P]),
+    "cdseg_vote_softmax_add": (_I, [_P, _P, _L, _I, _P, _P]),
+    "cdseg_argmax_rows": (_I, [_P, _L, _I, _P, _P]),
     "cdseg_gemm_tc": (_I, [_P, _L, _P, _I, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P, _L, _I, _P, _Z, _P]),
 }
 

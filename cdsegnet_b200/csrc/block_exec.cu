@@ -77,17 +77,21 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
       RUN(cdseg_small_linear(a->t_scene, a->t_W, a->t_b, 0, a->B, a->T_dim, C, tproj, stream));
       tp = tproj;
     }
+    if (a->ev[4]) cudaEventRecord((cudaEvent_t)a->ev[4], (cudaStream_t)stream);
     RUN(cdseg_pre_attn(a->conv_in ? a->conv_in : a->x, a->x, n, C, a->nbr, a->tile_mask, a->conv_plan, a->conv_Bp, a->conv_b, a->lin_Bp,
                        a->lin_b, a->cpe_g, a->cpe_b, tp, tp ? a->batch : nullptr, a->n1_g, a->n1_b, a->ln_eps, a->qkv_Bp, a->qkv_b, x1,
                        qkv, stream));
+    if (a->ev[5]) cudaEventRecord((cudaEvent_t)a->ev[5], (cudaStream_t)stream);
   } else {
   // cpe: conv (implicit GEMM over 27 taps) -> Linear -> LayerNorm
   {
     const int64_t tiles = ((n + 127) / 128) * ((C + 127) / 128);
     const int ns = pick_split(tiles, 27);
     if (cdseg_gemm_tc_workspace_bytes(n, C, ns) > ws_bytes) return CDSEG_ENOSPC;
+    if (a->ev[4]) cudaEventRecord((cudaEvent_t)a->ev[4], (cudaStream_t)stream);
     RUN(cdseg_gemm_tc(a->conv_in ? a->conv_in : a->x, C, a->nbr, 27, a->tile_mask, a->conv_Bp, n, C, C, a->conv_b, nullptr, 0, 0, y1, C,
                       ns, ws, ws_bytes, stream));
+    if (a->ev[5]) cudaEventRecord((cudaEvent_t)a->ev[5], (cudaStream_t)stream);
   }
   RUN(run_linear(y1, n, C, C, a->lin_Bp, a->lin_b, nullptr, 0, y2, ws, ws_bytes, stream));
   RUN(cdseg_add_layernorm(y2, nullptr, nullptr, nullptr, a->cpe_g, a->cpe_b, a->ln_eps, n, C, nullptr, y1, stream));

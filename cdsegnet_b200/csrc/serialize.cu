@@ -280,12 +280,12 @@ CDSEG_API size_t cdseg_argsort_workspace_bytes(int k, int64_t N) {
   return keys + vals + hist + 256;
 }
 
-// codes [k,N] int64 (non-negative), nbits = number of significant key bits.
+// codes [k,N] int64 compared as UNSIGNED 64-bit keys, nbits = number of significant key bits (<= 64).
 // order/inverse: int32 [k,N].  codes are left untouched.
 CDSEG_API int cdseg_argsort_rows(const int64_t* codes, int k, int64_t N, int nbits, int32_t* order,
                                  int32_t* inverse, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (k <= 0 || nbits < 0 || nbits > 63 || N >= (1ll << 31)) return CDSEG_EINVAL;
+  if (k <= 0 || nbits < 0 || nbits > 64 || N >= (1ll << 31)) return CDSEG_EINVAL;   // keys are compared as uint64
   if (N == 0) return CDSEG_OK;
   if (workspace_bytes < cdseg_argsort_workspace_bytes(k, N)) return CDSEG_ENOSPC;
   const int ntiles = (int)((N + RS_TILE - 1) / RS_TILE);

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import check
 
 ORDER_IDS = {"z": 0, "z-trans": 1, "hilbert": 2, "hilbert-trans": 3}
-PROFILE = None     # bench.py sets this to a list: per Block a dict(ev=[4 raw cudaEvent_t], n, C, H, pairs) (see Block._native)
+PROFILE = None     # bench.py sets this to a list: per Block a dict(ev=[6 raw cudaEvent_t], n, C, H, pairs, has_t) (see Block._native)
 
 
 def _p(t, dtype=None):
@@ -414,3 +414,46 @@ def axpy_scale_(y, x, a=1.0, scale=1.0):
     check(_lib.load().cdseg_axpy_scale(_p(y, torch.float32), _p(x, torch.float32), float(a), float(scale), y.numel(), _stream()),
           "axpy_scale")
     return y
+
+
+# ---------------------------------------------------------------- test-time fragment pipeline (fragments.cu)
+def grid_sample_plan(coord, grid_size, hash_type="fnv", legacy_f32=False):
+    """GridSample(mode="test") plan of one raw scene (transform.py:825-870).  coord fp32 or fp64 [n,3] on the device.
+    -> dict(grid_coord int32 [n,3], key int64 [n], order int32 [n], inverse int32 [n], start int32 [V+1], count int32 [V],
+            n_voxels, n_fragments, min_grid [3])  -- ONE host sync (8 ints) to learn V and F."""
+    lib = _lib.load()
+    n = coord.shape[0]
+    dev = coord.device
+    i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
+    grid, key, order, vox, start, count, stats = i32(n, 3), torch.empty(n, dtype=torch.int64, device=dev), i32(n), i32(n), i32(n + 1), i32(n), i32(8)
+    nb = lib.cdseg_grid_sample_workspace_bytes(n)
+    ws = _ws(nb, dev)
+    if coord.dtype not in (torch.float32, torch.float64):
+        raise _lib.CdsegError(f"coord must be float32 or float64, got {coord.dtype}")
+    check(lib.cdseg_grid_sample_plan(_p(coord), int(coord.dtype is torch.float64), n, float(grid_size), int(hash_type == "fnv"), int(bool(legacy_f32)),
+                                     _p(grid), _p(key), _p(order), _p(vox), _p(start), _p(count), _p(stats), _p(ws), nb, _stream()),
+          "grid_sample_plan")
+    st = stats.cpu().tolist()
+    V, F = st[0], st[1]
+    return dict(grid_coord=grid, key=key, order=order, inverse=vox, start=start[:V + 1], count=count[:V], n_voxels=V, n_fragments=F,
+                min_grid=st[2:5])
+
+
+def fragment_index(order, start, n_voxels, n_fragments):
+    """int32 [F, V]: row f = the `index` of fragment f"""
+    index = torch.empty((n_fragments, n_voxels), dtype=torch.int32, device=order.device)
+    check(_lib.load().cdseg_fragment_index(_p(order, torch.int32), _p(start, torch.int32), n_voxels, n_fragments, _p(index), _stream()),
+          "fragment_index")
+    return index
+
+
+def vote_softmax_add_(pred, logits, index):
+    check(_lib.load().cdseg_vote_softmax_add(_p(logits, torch.float32), _p(index, torch.int32), logits.shape[0], logits.shape[1],
+                                             _p(pred, torch.float32), _stream()), "vote_softmax_add")
+    return pred
+
+
+def argmax_rows(x):
+    out = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
+    check(_lib.load().cdseg_argmax_rows(_p(x, torch.float32), x.shape[0], x.shape[1], _p(out), _stream()), "argmax_rows")
+    return out

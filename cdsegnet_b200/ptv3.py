@@ -259,11 +259,11 @@ class Block(nn.Module):
         arena = ops.arena(need, x.device)
         out = torch.empty_like(x)
         a.out, a.scratch, a.scratch_bytes = out.data_ptr(), arena.data_ptr(), arena.numel()
-        if ops.PROFILE is not None:      # bench.py: time the attention kernel and the fc1 GEMM of this block with CUDA events
-            ev = [lib.cdseg_event_create() for _ in range(4)]
-            for i in range(4):
+        if ops.PROFILE is not None:      # bench.py: time the pre-attention, attention and post-attention kernels with CUDA events
+            ev = [lib.cdseg_event_create() for _ in range(6)]
+            for i in range(6):
                 a.ev[i] = ev[i]
-            ops.PROFILE.append(dict(ev=ev, n=n, C=C, H=a.H, pairs=pm["pairs"]))
+            ops.PROFILE.append(dict(ev=ev, n=n, C=C, H=a.H, pairs=pm["pairs"], has_t=ts is not None))
         check(lib.cdseg_block_forward(ctypes.byref(a), ops._stream()), "block_forward")
         point["feat"] = out
         return point

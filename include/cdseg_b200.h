@@ -183,7 +183,8 @@ typedef struct CdsegBlockArgs {
   const float* n2_g; const float* n2_b; const float* fc1_Bp; const float* fc1_b; const float* fc2_Bp; const float* fc2_b;
   float ln_eps;
   float* out; void* scratch; size_t scratch_bytes; /* out [n,C]; scratch >= cdseg_block_scratch_bytes(...) */
-  void* ev[4];                                    /* optional cudaEvent_t: recorded before/after the attention kernel and before/after fc1 */
+  void* ev[6];                                    /* optional cudaEvent_t pairs recorded around: [0,1] the attention kernel, [2,3] the post-attention
+                                                     kernel (fc1 GEMM on the unfused path), [4,5] the pre-attention kernel (cpe conv GEMM when unfused) */
 } CdsegBlockArgs;
 size_t cdseg_block_scratch_bytes(int64_t n, int C, int H, int T, int Kp, int B);
 int cdseg_block_forward(const CdsegBlockArgs* args, void* stream);
@@ -212,6 +213,26 @@ int cdseg_ddim_step(const float* x_t, const float* pred, int64_t total, float sq
                     float sqrt_1mab_prev, int target_is_x0, int last, float* out, void* stream);
 /* y = (y + a * x) * scale  (the "avg" accumulation of inference_ddim, default.py:342, 359) */
 int cdseg_axpy_scale(float* y, const float* x, float a, float scale, int64_t total, void* stream);
+
+/* ---- test-time fragment pipeline --------------------------------------------------------------
+ * GridSample(mode="test"), pointcept/datasets/transform.py:796-933: grid = floor(coord / grid_size) - min; key = FNV64-1A
+ * (hash_fnv != 0) or the ravel hash of grid; order = stable argsort(key) (the reference's np.argsort leaves the order of
+ * points inside one voxel unspecified; this library fixes it to ascending point index); voxel_of_point = GridSample's
+ * `inverse`; start int32 [n + 1] (first V + 1 entries used, start[V] = n) and count int32 [n] (first V used) describe the
+ * runs; stats int32 [8] on the device: [0] V = voxels, [1] F = max count = number of fragments, [2..4] / [5..7] min / max of
+ * floor(coord / grid_size).  legacy_f32 != 0 divides in float32 (NumPy 1.x value-based casting of np.array(grid_size));
+ * 0 divides in float64 (NumPy >= 2).  coord fp32 [n,3], or fp64 [n,3] with coord_f64 != 0 (the TTA rotations of transform.py:259-294
+ * leave float64 coordinates); grid int32 [n,3]; key int64 [n] (uint64 bit pattern). */
+size_t cdseg_grid_sample_workspace_bytes(int64_t n);
+int cdseg_grid_sample_plan(const void* coord, int coord_f64, int64_t n, double grid_size, int hash_fnv, int legacy_f32, int32_t* grid,
+                           int64_t* key, int32_t* order, int32_t* voxel_of_point, int32_t* start, int32_t* count,
+                           int32_t* stats, void* workspace, size_t workspace_bytes, void* stream);
+/* index[f][v] = order[start[v] + f % count[v]] for f < F, v < V: row f is fragment f's `index` (transform.py:868-870) */
+int cdseg_fragment_index(const int32_t* order, const int32_t* start, int V, int F, int32_t* index, void* stream);
+/* vote accumulation, pointcept/engines/test.py:252-257: pred[index[r], :] += softmax(logits[r, :]) */
+int cdseg_vote_softmax_add(const float* logits, const int32_t* index, int64_t n, int C, float* pred, void* stream);
+/* out[r] = argmax_c x[r, c] (lowest index on ties), test.py:268 */
+int cdseg_argmax_rows(const float* x, int64_t n, int C, int64_t* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,57 @@
+"""CPU suite for the fragment pipeline (§8(f) rank 1): oracle/fragments_np.py against the outputs of the reference's own
+GridSample / collate_fn (tests/golden/fragments.npz, made by tests/golden/make_golden_fragments.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import fragments_np as F
+
+Z = np.load(os.path.join(GOLDEN, "fragments.npz"))
+
+
+def test_fnv_known_answers():
+    """FNV64-1A as the reference writes it (multiply, then xor): offset basis for an empty row, hand-computed single column"""
+    assert F.fnv_hash_vec(np.zeros((1, 0), dtype=np.int64))[0] == np.uint64(14695981039346656037)
+    h = (14695981039346656037 * 1099511628211) % 2 ** 64 ^ 5
+    assert F.fnv_hash_vec(np.array([[5]]))[0] == np.uint64(h)
+
+
+def check_plan_against_reference(i, plan, index):
+    """everything GridSample determines; `index` rows may differ from the reference only by WHICH point of a voxel comes when"""
+    n = len(Z[f"c{i}_coord"])
+    assert np.array_equal(np.asarray(plan["grid_coord"]), Z[f"c{i}_grid"])
+    assert np.array_equal(np.asarray(plan["key"]).astype(np.uint64), Z[f"c{i}_key"])
+    assert np.array_equal(np.asarray(plan["inverse"]), Z[f"c{i}_inverse"])
+    ref_index = Z[f"c{i}_index"]
+    assert index.shape == ref_index.shape
+    inv = Z[f"c{i}_inverse"]
+    V = inv.max() + 1
+    for f in range(len(index)):
+        assert np.array_equal(inv[index[f]], np.arange(V))              # fragment f holds exactly one point of every voxel, in voxel order
+        assert np.array_equal(inv[ref_index[f]], np.arange(V))
+        assert np.array_equal(Z[f"c{i}_grid"][index[f]], Z[f"c{i}_part_grid"][f])   # its grid_coord is therefore identical
+    for arr in (index, ref_index):
+        assert np.array_equal(np.unique(arr), np.arange(n))              # all fragments together cover every point
+    # per voxel, the points visited over the fragments form the same multiset up to the cyclic start the tie order implies
+    cnt = np.bincount(inv)
+    for v in np.random.default_rng(0).choice(V, size=min(V, 200), replace=False):
+        assert sorted(set(index[:, v])) == sorted(set(ref_index[:, v])) == sorted(np.flatnonzero(inv == v))
+        assert len(set(index[:cnt[v], v])) == cnt[v]
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_oracle_plan_vs_reference(i):
+    plan = F.grid_sample_plan(Z[f"c{i}_coord"], float(Z[f"c{i}_grid_size"]), str(Z[f"c{i}_hash"]))
+    check_plan_against_reference(i, plan, F.fragment_index(plan))
+
+
+def test_oracle_vote():
+    rng = np.random.default_rng(1)
+    frags = [(rng.permutation(50)[:30], rng.standard_normal((30, 5)).astype(np.float32)) for _ in range(4)]
+    pred, labels = F.vote(50, 5, frags)
+    ref = np.zeros((50, 5))
+    for idx, lg in frags:
+        e = np.exp(lg.astype(np.float64)); ref[idx] += e / e.sum(1, keepdims=True)
+    assert np.allclose(pred, ref) and np.array_equal(labels, ref.argmax(1))
