@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
-SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "losses.cu", "fragments.cu"]
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "losses.cu", "fragments.cu", "knn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
@@ -133,6 +133,8 @@ SIGNATURES = {
     "cdseg_fragment_index": (_I, [_P, _P, _I, _I, _P, _P]),
     "cdseg_vote_softmax_add": (_I, [_P, _P, _L, _I, _P, _P]),
     "cdseg_argmax_rows": (_I, [_P, _L, _I, _P, _P]),
+    "cdseg_knn_workspace_bytes": (_Z, [_L]),
+    "cdseg_knn_query": (_I, [_I, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _Z, _P]),
     "cdseg_gemm_tc": (_I, [_P, _L, _P, _I, _P, _P, _L, _I, _I, _P, _P, _L, _I, _P, _L, _I, _P, _Z, _P]),
 }
 

@@ -234,6 +234,18 @@ int cdseg_vote_softmax_add(const float* logits, const int32_t* index, int64_t n,
 /* out[r] = argmax_c x[r, c] (lowest index on ties), test.py:268 */
 int cdseg_argmax_rows(const float* x, int64_t n, int C, int64_t* out, void* stream);
 
+/* ---- pointops.knn_query ---------------------------------------------------------------------------
+ * Replaces knn_query_cuda_launcher(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2)
+ * (libs/pointops/src/knn_query/knn_query_cuda_kernel.h:13, kernel .cu:60-104): for each of the m query points new_xyz fp32
+ * [m,3] the nsample (<= 128) nearest points of xyz fp32 [n,3] inside the same batch (offset / new_offset int32 [B],
+ * cumulative), idx int32 [m,nsample] ascending by squared distance (-1 = batch smaller than nsample), dist2 fp32
+ * [m,nsample] SQUARED distances (1e10 for missing) -- the Python wrapper takes the sqrt like functions/query.py:26.
+ * Exact (uniform cell grid + shell search instead of the reference's O(m n) scan); ties go to the lower point index.
+ * Added to the reference signature: B, n, a caller-allocated workspace, the stream and the int status. */
+size_t cdseg_knn_workspace_bytes(int64_t n);
+int cdseg_knn_query(int m, int nsample, const float* xyz, const float* new_xyz, const int32_t* offset, const int32_t* new_offset,
+                    int B, int64_t n, int32_t* idx, float* dist2, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,3 +55,15 @@ def test_oracle_vote():
     for idx, lg in frags:
         e = np.exp(lg.astype(np.float64)); ref[idx] += e / e.sum(1, keepdims=True)
     assert np.allclose(pred, ref) and np.array_equal(labels, ref.argmax(1))
+
+
+def test_knn_oracle_small_known_answers():
+    from oracle import knn_np as K
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [0, 2, 0], [5, 5, 5], [5, 5, 6]], dtype=np.float32)
+    off = np.array([3, 5], dtype=np.int32)
+    q = np.array([[0.9, 0, 0], [5, 5, 5.4]], dtype=np.float32)
+    idx, d2 = K.knn_query(2, xyz, off, q, np.array([1, 2], dtype=np.int32))
+    assert idx.tolist() == [[1, 0], [3, 4]]                       # neighbours never cross the batch boundary
+    assert np.allclose(d2, [[0.01, 0.81], [0.16, 0.36]], atol=1e-6)
+    idx, d2 = K.knn_query(4, xyz, off, q, np.array([1, 2], dtype=np.int32))
+    assert idx.tolist() == [[1, 0, 2, -1], [3, 4, -1, -1]] and d2[1, 2] == np.float32(1e10)
