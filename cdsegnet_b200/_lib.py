@@ -114,6 +114,7 @@ SIGNATURES = {
     "cdseg_gemm_tc_set_trace": (None, [_P, _I]),
     "cdseg_post_attn": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
     "cdseg_pre_attn": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
+    "cdseg_pre_attn_set_trace": (None, [_P, _I]),
     "cdseg_conv_plan_bytes": (_Z, [_L]),
     "cdseg_conv_tile_plan": (_I, [_P, _L, _P, _P]),
     "cdseg_set_fused_mask": (None, [_I]),

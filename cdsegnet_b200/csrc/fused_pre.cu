@@ -45,6 +45,7 @@ struct PreParams {
   const __half *Bp_conv, *Bp_lin, *Bp_qkv;
   const float *b_conv, *b_lin, *cpe_g, *cpe_b, *n1_g, *n1_b, *b_qkv;
   const float* tproj; const int32_t* batch;     // [B, C] per-scene timestep projection + scene id per row, or NULL
+  long long* trace; int trace_cta;              // profiling hook (cdseg_pre_attn_set_trace): clock64 stamps of one CTA, null in production
 };
 
 struct PreBars {
@@ -118,7 +119,12 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
       if (lane == 0) { tma_store_2d(tm, col, row0, smem_u32(stg)); bulk_commit(); }
     };
 
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const bool tr = p.trace && (int)blockIdx.x == p.trace_cta && threadIdx.x == 0;
+    int tn = 0;                                                    // 12 stamps per tile: see profiles/trace_pre.py
+    long long w_empty = 0, w_gather = 0, w_st = 0;                 // tap-loop split of the traced thread: a_empty waits / gather + store issue / wait::st + arrive
+#define STAMP(k) do { if (tr && tn < 6) p.trace[tn * 12 + (k)] = clock64(); } while (0)
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tn) {
+      STAMP(0);
       const long long m = (long long)tile * BM + r;
       const int row0 = tile * BM + warp * 32;
       const int U = __ldg(reinterpret_cast<const int*>(p.plan + (size_t)tile * Q_REC));
@@ -131,6 +137,7 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
           mbar_wait(smem_u32(&bars->fill_full), fill_cnt & 1);
           ++fill_cnt;
         }
+        if (kc == 0) STAMP(1);
         if (cached) {
           for (int u = r; u < U; u += BM) {                      // raw fp32 row -> [hi 16 words | lo 16 words], same swizzled chunks
             uint8_t* row = s_cache + u * 128;
@@ -150,7 +157,9 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+        if (kc == 0) STAMP(2);
         for (uint32_t mk = tmask; mk; mk &= mk - 1, ++a_it) {
+          const long long c1 = tr ? clock64() : 0;
           const int t = __ffs(mk) - 1;
           uint32_t w[32];
           if (cached) {
@@ -186,20 +195,25 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
             }
           }
           const int q = a_it % Q_AT;
+          const long long c0 = tr ? clock64() : 0;
           if (a_it >= Q_AT) { mbar_wait(smem_u32(&bars->a_empty[q]), ((a_it / Q_AT) - 1) & 1); tc_fence_after(); }
+          const long long c2 = tr ? clock64() : 0;
           tmem_st16(RING + lb + q * 32, w);
           tmem_st16(RING + lb + q * 32 + 16, w + 16);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&bars->a_full[q]));
+          if (tr) { w_gather += c0 - c1; w_empty += c2 - c0; w_st += clock64() - c2; }
         }
         if (cached || kc == nc - 1) {
           fence_async_smem();                                    // the next fill / x box (async proxy) overwrites what was read and written here
           mbar_arrive(smem_u32(&bars->cache_free));
         }
       }
+      STAMP(3);
       // ---- conv + bias -> A operand of the cpe Linear, in place
       acc_wait();
+      STAMP(4);
       for (int c = 0; c < nc; ++c) {
         uint32_t a[32];
         tmem_ld32(ACCC + lb + c * 32, a);
@@ -209,8 +223,10 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
         split_store(v, ACCC + lb + c * 32);
         operand_ready(c);
       }
+      STAMP(5);
       // ---- u = lin + b: LayerNorm_cpe statistics
       acc_wait();
+      STAMP(6);
       float u0 = 0.f, s1 = 0.f, s2 = 0.f;
       for (int c = 0; c < nc; ++c) {
         uint32_t a[32];
@@ -254,6 +270,7 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
         store_box(&tmX1, c * 32, row0, v);
       }
       tmem_st_wait();
+      STAMP(7);
       const float dm2 = t1 * inv_c, mean2 = w0 + dm2;
       const float rstd2 = rsqrtf(fmaxf(t2 * inv_c - dm2 * dm2, 0.f) + p.eps);
       // ---- h = LayerNorm_1(x1) -> A operand of the qkv GEMM, in place
@@ -266,9 +283,11 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
         split_store(v, ACCL + lb + c * 32);
         operand_ready(c);
       }
+      STAMP(8);
       // ---- qkv chunks: + bias -> TMA store
       for (int j = 0; j < nq; ++j) {
         acc_wait();
+        if (j == 0) STAMP(9);
         const int un = min(128, 3 * C - 128 * j);
         for (int c = 0; c < un / 32; ++c) {
           uint32_t a[32];
@@ -282,10 +301,14 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
       }
       tc_fence_before();
       // ---- the staging boxes live in the cache bytes: the next tile's fill may start once the stores have read them
+      STAMP(10);
       if (lane == 0) bulk_wait_read<0>();
       __syncwarp();
       mbar_arrive(smem_u32(&bars->cache_free));
+      STAMP(11);
+      if (tr && tn < 6) { p.trace[72 + tn * 3] = w_empty; p.trace[73 + tn * 3] = w_gather; p.trace[74 + tn * 3] = w_st; w_empty = w_gather = w_st = 0; }
     }
+#undef STAMP
   } else if (warp == 4) {
     // =========================================== input loader ===========================================
     uint32_t free_cnt = 0, x_it = 0;
@@ -466,6 +489,10 @@ __global__ void __launch_bounds__(BM) conv_tile_plan_kernel(const int32_t* __res
 
 }  // namespace fz
 
+static long long* g_pre_trace = nullptr;
+static int g_pre_trace_cta = 0;
+CDSEG_API void cdseg_pre_attn_set_trace(long long* buf, int cta) { g_pre_trace = buf; g_pre_trace_cta = cta; }
+
 static int sm_count_pre() {
   static int n = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
   return n;
@@ -504,6 +531,7 @@ CDSEG_API int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, in
   p.Bp_qkv = reinterpret_cast<const __half*>(qkv_Bp);
   p.b_conv = conv_b; p.b_lin = lin_b; p.cpe_g = cpe_g; p.cpe_b = cpe_b; p.n1_g = n1_g; p.n1_b = n1_b; p.b_qkv = qkv_b;
   p.tproj = tproj; p.batch = batch;
+  p.trace = g_pre_trace; p.trace_cta = g_pre_trace_cta;
   const int per_sm = C <= 64 ? 2 : 1;
   size_t smem = (size_t)fz::Q_CACHE + (size_t)fz::Q_SB * fz::B_STAGE + fz::Q_LIDX + fz::Q_PAR * 4 + sizeof(fz::PreBars) + 1024;
   if (per_sm == 1) smem = smem > 120 * 1024 ? smem : 120 * 1024;

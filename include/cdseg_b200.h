@@ -163,6 +163,8 @@ int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, int C, const
  * (-1 padded), int16 lidx[128][27] (-1 = absent).  ucount > UCAP marks a tile whose neighbourhood does not fit (its uniq /
  * lidx are not written; consumers read nbr directly for it).  plan: >= cdseg_conv_plan_bytes(n) bytes, 16-byte aligned. */
 #define CDSEG_CONV_PLAN_UCAP 384
+/* profiling hook: clock64 stamps (12 per tile, first 6 tiles) of row thread 0 of CTA `cta` of later cdseg_pre_attn launches; NULL = off */
+void cdseg_pre_attn_set_trace(long long* buf, int cta);
 size_t cdseg_conv_plan_bytes(int64_t n);
 int cdseg_conv_tile_plan(const int32_t* nbr, int64_t n, void* plan, void* stream);
 /* which fused kernels cdseg_block_forward uses: bit 0 post-attention chain, bit 1 pre-attention chain (default: all) */

@@ -138,3 +138,66 @@ def test_single_stream_mode_matches():
             torch.cuda.synchronize()
             assert np.abs(n["feat"].cpu().numpy() - z["n_feat"]).max() < 1e-3
             assert np.abs(c["feat"].cpu().numpy() - z["c_feat"]).max() < 1e-3
+
+
+def _oracle_case(scene, cfg_over, cap=64, seed=11):
+    """small dual network on an arbitrary synthetic batch: (cfg, shapes, noise, perms, oracle c/n logits)"""
+    import os, sys
+    import cdsegnet_b200 as cb
+    from oracle import ptv3_oracle as O
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as MG
+    cfg = dict(MG.SMALL_CFG)
+    ps = MG.patch_sizes_for(scene, cap)
+    cfg.update(n_enc_patch_size=tuple(ps), n_dec_patch_size=tuple(ps[:4]), c_enc_patch_size=(ps[0], ps[2], ps[4]),
+               c_dec_patch_size=(ps[0], ps[2]))
+    cfg.update(cfg_over)
+    m = cb.PointTransformerV3(**cfg)
+    shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+    sd = synth_state_dict(shapes)
+    m.load_state_dict(sd, strict=True)
+    n = len(scene["coord"])
+    rng = np.random.default_rng(seed)
+    noise = rng.standard_normal((n, cfg["c_in_channels"])).astype(np.float32)
+    perms = [rng.permutation(4) for _ in range(6)]
+    base = dict(coord=t(scene["coord"]), grid_coord=t(scene["grid_coord"]).long(), offset=t(scene["offset"]))
+    ts = 999 * torch.ones((n, 1), dtype=torch.int64)
+    c_ref, n_ref = O.forward(sd, cfg, dict(base, feat=t(noise), t_emb=O.calc_t_emb(ts, cfg["T_dim"])), dict(base, feat=t(scene["feat"])),
+                             attn_mode="dense", perm_fn=replay(perms))
+    return m, cfg, noise, perms, c_ref["feat"].numpy(), n_ref["feat"].numpy()
+
+
+def _run(m, cfg, scene, noise, perms):
+    from cdsegnet_b200.segmentor import calc_t_emb
+    m = m.to(DEV).eval()
+    base = dict(coord=t(scene["coord"]).to(DEV), grid_coord=t(scene["grid_coord"]).to(DEV), offset=t(scene["offset"]).to(DEV))
+    B = len(scene["offset"])
+    ts = 999 * torch.ones((B, 1), dtype=torch.int64, device=DEV)
+    c, n = m(dict(base, feat=t(noise).to(DEV), t_emb=calc_t_emb(ts, cfg["T_dim"])), dict(base, feat=t(scene["feat"]).to(DEV)),
+             perm_fn=replay(perms))
+    torch.cuda.synchronize()
+    return c["feat"].cpu().numpy(), n["feat"].cpu().numpy()
+
+
+@pytest.mark.timeout(300)
+def test_nuscenes_shaped_batch_matches_oracle():
+    """BASELINE config 4 shape: outdoor sweeps, 4 input channels (coord + strength), 16 classes, grid 0.05 m => depth 11
+    serialization keys, a batch of sweeps -- exact-attention logits within 1e-3 of the oracle"""
+    from cdsegnet_b200 import synth
+    scene = synth.collate([synth.nuscenes_sweep(5000, s) for s in (0, 1, 2)])
+    assert int(scene["grid_coord"].max()) >= 1024                       # depth 11
+    m, cfg, noise, perms, c_ref, n_ref = _oracle_case(scene, dict(c_in_channels=4, n_in_channels=4, num_classes=16, enable_flash=False))
+    c, n = _run(m, cfg, scene, noise, perms)
+    assert n.shape == (len(scene["coord"]), 16) and c.shape[1] == 4
+    assert np.abs(n - n_ref).max() < 1e-3 and np.abs(c - c_ref).max() < 1e-3
+
+
+@pytest.mark.timeout(300)
+def test_batch8_ragged_scenes_match_oracle():
+    """BASELINE config 3 shape (inference side): a batch of 8 scenes of different sizes, one of them smaller than a patch"""
+    from cdsegnet_b200 import synth
+    sizes = (2600, 1900, 900, 3100, 700, 1500, 40, 2200)
+    scene = synth.collate([synth.scannet_scene(s, 20 + i, room_m=(3.0, 2.4, 1.6), n_boxes=2) for i, s in enumerate(sizes)])
+    m, cfg, noise, perms, c_ref, n_ref = _oracle_case(scene, dict(enable_flash=False), cap=32)
+    c, n = _run(m, cfg, scene, noise, perms)
+    assert np.abs(n - n_ref).max() < 1e-3 and np.abs(c - c_ref).max() < 1e-3
