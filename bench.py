@@ -26,37 +26,60 @@ METRIC = "points/sec (120k-point ScanNet-shaped scene, full CDSegNet single-step
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Reads NVML in-process (nvidia_ml_py:
+    microseconds per sample, no child process competing with the enqueue thread for a core -- spawning nvidia-smi every
+    200 ms from every rank cost the 2-GPU run measurable step time); falls back to the recipe's nvidia-smi query line."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.nvml, self.source = index, [], False, None, "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [n.nvmlClocksThrottleReasonHwSlowdown, n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                n.nvmlClocksThrottleReasonSwThermalSlowdown, n.nvmlClocksThrottleReasonSwPowerCap]
+        return [str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag = True
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for nme, v in zip(names, r[3:7]):
+            for nme, v in zip(self.NAMES, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         mx = max((float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()), default=None)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": self.source}
 
 
 def peaks():
@@ -199,6 +222,8 @@ def run_cuda(args):
         logits_host.copy_(out, non_blocking=True)
         return out
 
+    rank_ms = {}
+
     def timed(fn, steps, warmup, profile_attn=False):
         for _ in range(warmup):
             fn()
@@ -226,6 +251,9 @@ def run_cuda(args):
         ops.PROFILE = None
         tsum = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
+            allr = [torch.zeros_like(tsum) for _ in range(world)]
+            dist.all_gather(allr, tsum)
+            rank_ms[fn.__name__] = [float(a.item()) / steps for a in allr]
             dist.all_reduce(tsum, op=dist.ReduceOp.MAX)
         return float(tsum.item()), launches, wall, prof
 
@@ -319,6 +347,8 @@ def run_cuda(args):
                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) + n * 6 * 4),
                     "d2h_bytes_per_step": int(n * 20 * 4), "ms_per_step": ms_e2e / args.steps},
             "roofline": roof, "roofline_attention": attn, "roofline_post": post}
+    if world > 1:
+        line["ms_per_step_by_rank"] = rank_ms.get("step_resident")
     if rank == 0:
         if world == 1 and not args.no_cpu:
             npts = reference_points(args)
