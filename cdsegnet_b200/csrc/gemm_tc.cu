@@ -102,6 +102,7 @@ struct Params {
   const float* bias; const float* res; long long ldr; int act;
   float* out; long long ldo;
   float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
+  int nw;                                 // output-tile width in columns (32 / 64 / 128): a CTA owns columns [blockIdx.y * nw, + nw)
   int vec_ok;                             // output / residual rows are 16-byte aligned
   int AT, SB, b_bytes, acc_cols, tmem_cols;   // A ring slots (TMEM), B ring stages (smem), bytes of one B block, TMEM layout
   long long* trace; int trace_cta;        // profiling hook: clock64 stamps of one CTA (null in production)
@@ -146,8 +147,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x, tile_n = blockIdx.y, z = blockIdx.z;
   const int ntiles = (p.N + NT - 1) / NT;
-  const int n0 = tile_n * NT;
-  const int wn = min(NT, p.N - n0);                 // valid output columns of this tile
+  const int n0 = tile_n * p.nw;
+  const int wn = min(p.nw, p.N - n0);               // valid output columns of this tile
   const int un = (wn + 15) & ~15;                   // UMMA N (multiple of 16)
   const int kch = (p.K + KC - 1) / KC;
   const int t_begin = (int)((long long)p.T * z / p.nsplit), t_end = (int)((long long)p.T * (z + 1) / p.nsplit);
@@ -359,7 +360,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
         const int t = tap_of(it), kc = it - (it / kch) * kch;
         const int s = it % SB, u = it / SB;
         if (u > 0) mbar_wait(smem_u32(&bars->empty_b[s]), (uint32_t)((u - 1) & 1));
-        const __half* blk = reinterpret_cast<const __half*>(p.Bp) + ((((long long)t * kch + kc) * ntiles + tile_n) * 2) * (NT * KC);
+        // packed block of the 128-column group this tile lies in; a narrower tile starts (n0 % NT) / 8 row-groups of 8 n x 32 k into it
+        const __half* blk = reinterpret_cast<const __half*>(p.Bp) + ((((long long)t * kch + kc) * ntiles + n0 / NT) * 2) * (NT * KC) + (n0 % NT) * KC;
         uint8_t* b_hi = s_b + (size_t)s * 2 * B_BYTES;
         mbar_expect_tx(smem_u32(&bars->full_b[s]), 2 * bbytes);
         tma_load_1d(smem_u32(b_hi), blk, bbytes, smem_u32(&bars->full_b[s]));
@@ -482,6 +484,9 @@ CDSEG_API int cdseg_tile_tap_mask(const int32_t* nbr, int64_t M, int T, uint32_t
   return CDSEG_OK;
 }
 
+// A/B switch, OFF by default: measured on the full step (profiles/r01f_narrow_tiles.md) narrow tiles lose to split-K + reduce
+// (12.01 vs 11.76 ms): every CTA re-reads the whole A row block and N = 32 MMAs run at a third of the N = 128 rate
+static const bool g_narrow = [] { const char* e = getenv("CDSEG_GEMM_NARROW"); return e && atoi(e) != 0; }();
 static long long* g_trace = nullptr;
 static int g_trace_cta = 0;
 // profiling hook: clock64 stamps of CTA (cta,0,0) of subsequent launches into a device buffer of >= 16 int64; NULL disables
@@ -502,7 +507,16 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
     return CDSEG_EINVAL;
   if (M == 0) return CDSEG_OK;
   if (workspace_bytes < cdseg_gemm_tc_workspace_bytes(M, N, nsplit)) return CDSEG_ENOSPC;
-  const int un_max = N >= gt::NT ? gt::NT : ((N + 15) & ~15);
+  // Experiment (CDSEG_GEMM_NARROW=1): a dense Linear whose caller asked for a K split (few row tiles, K >= 256) served by
+  // narrower output tiles instead -- the same number of CTAs, no partial sums, no reduce launch.
+  // (T, K) chunks of a contiguous row are the same operand as (1, T * K): the packed weight order [t][kc][tile] is unchanged.
+  int nw = gt::NT;
+  if (!idx && !sub && nsplit > 1 && (long long)T * K <= 1024 && (N % 32) == 0 && g_narrow) {
+    K *= T; T = 1; nsplit = 1;
+    const long long tm = (M + gt::BM - 1) / gt::BM;
+    while (nw > 32 && tm * ((N + nw - 1) / nw) < 120) nw >>= 1;
+  }
+  const int un_max = N >= nw ? nw : ((N + 15) & ~15);
   const int b_bytes = un_max * gt::KC * 2;
   const int iters = (int)((long long)T * ((K + gt::KC - 1) / gt::KC) / nsplit);      // upper bound of k-iterations per CTA
   // TMEM: accumulator columns + A ring (32 columns per slot); allocation must be a power of two >= 32
@@ -527,12 +541,12 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   gt::Params p;
   p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp; p.sub = sub; p.taps_ld = taps_ld;
   p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.res = res; p.ldr = ldr; p.act = act; p.out = out; p.ldo = ldo;
-  p.part = (float*)workspace; p.nsplit = nsplit;
+  p.part = (float*)workspace; p.nsplit = nsplit; p.nw = nw;
   p.AT = AT; p.SB = SB; p.b_bytes = b_bytes; p.acc_cols = acc_cols; p.tmem_cols = tmem_cols;
   p.trace = g_trace; p.trace_cta = g_trace_cta;
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
-  dim3 g(cdseg_div_up(M, gt::BM), (N + gt::NT - 1) / gt::NT, nsplit);
+  dim3 g(cdseg_div_up(M, gt::BM), (N + nw - 1) / nw, nsplit);
   if (dense3) gt::gemm_tc_kernel<3><<<g, gt::NTHREADS, smem, st>>>(p);
   else gt::gemm_tc_kernel<2><<<g, gt::NTHREADS, smem, st>>>(p);
   CDSEG_COUNT_LAUNCH(1);

@@ -295,7 +295,10 @@ def test_attention_tcgen05_vs_real_flash_attn(ops, counts, K, H):
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("M,K,N,act,use_res,T", [(1000, 32, 96, 0, False, 1), (5000, 32, 128, 1, False, 1), (129, 16, 16, 0, True, 1),
                                                   (300, 64, 20, 0, False, 1), (777, 96, 288, 1, True, 1), (816, 2048, 512, 0, True, 32),
-                                                  (816, 512, 1536, 0, False, 8), (3023, 256, 1024, 1, False, 1), (1, 64, 6, 0, False, 1)])
+                                                  (816, 512, 1536, 0, False, 8), (3023, 256, 1024, 1, False, 1), (1, 64, 6, 0, False, 1),
+                                                  # few row tiles + K split requested: served by narrow (32 / 64 column) output tiles, no partial sums
+                                                  (990, 512, 512, 1, True, 8), (3800, 256, 256, 0, True, 4), (3800, 1024, 256, 0, True, 16),
+                                                  (990, 512, 96, 0, False, 8), (300, 256, 160, 1, True, 4)])
 def test_gemm_tc_linear_vs_fp64(ops, M, K, N, act, use_res, T):
     """fp32-faithful: 3xTF32 split keeps the result within ~1e-5 relative of an fp64 reference (cuBLAS SGEMM class)"""
     gen = torch.Generator().manual_seed(M + K + N)
