@@ -112,6 +112,7 @@ SIGNATURES = {
     "cdseg_tile_tap_mask": (_I, [_P, _L, _I, _P, _P]),
     "cdseg_gemm_tc_workspace_bytes": (_Z, [_L, _I, _I]),
     "cdseg_gemm_tc_set_trace": (None, [_P, _I]),
+    "cdseg_gemm_tc_set_narrow": (None, [_I]),
     "cdseg_post_attn": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
     "cdseg_pre_attn": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
     "cdseg_pre_attn_set_trace": (None, [_P, _I]),

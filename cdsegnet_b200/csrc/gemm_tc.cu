@@ -486,7 +486,8 @@ CDSEG_API int cdseg_tile_tap_mask(const int32_t* nbr, int64_t M, int T, uint32_t
 
 // A/B switch, OFF by default: measured on the full step (profiles/r01f_narrow_tiles.md) narrow tiles lose to split-K + reduce
 // (12.01 vs 11.76 ms): every CTA re-reads the whole A row block and N = 32 MMAs run at a third of the N = 128 rate
-static const bool g_narrow = [] { const char* e = getenv("CDSEG_GEMM_NARROW"); return e && atoi(e) != 0; }();
+static bool g_narrow = [] { const char* e = getenv("CDSEG_GEMM_NARROW"); return e && atoi(e) != 0; }();
+CDSEG_API void cdseg_gemm_tc_set_narrow(int on) { g_narrow = on != 0; }
 static long long* g_trace = nullptr;
 static int g_trace_cta = 0;
 // profiling hook: clock64 stamps of CTA (cta,0,0) of subsequent launches into a device buffer of >= 16 int64; NULL disables

@@ -131,6 +131,9 @@ int cdseg_tile_tap_mask(const int32_t* nbr, int64_t M, int T, uint32_t* mask, vo
  * taps; act 0 none / 1 GELU(erf); nsplit > 1 splits the taps over grid.z (partials in workspace, reduced by a 2nd kernel) */
 size_t cdseg_gemm_tc_workspace_bytes(int64_t M, int N, int nsplit);
 /* profiling hook: clock64 stamps of CTA (cta,0,0) of subsequent launches into a device buffer of >= 16 int64; NULL disables */
+/* experiment switch (default off, env CDSEG_GEMM_NARROW): serve a dense Linear that was asked to split K with 32 / 64-column
+ * output tiles instead of partial sums + a reduce launch (profiles/r01f_narrow_tiles.md) */
+void cdseg_gemm_tc_set_narrow(int on);
 void cdseg_gemm_tc_set_trace(long long* buf, int cta);
 int cdseg_gemm_tc(const float* A, int64_t lda, const int32_t* idx, int T, const uint32_t* tile_mask, const float* Bp,
                   int64_t M, int N, int K, const float* bias, const float* res, int64_t ldr, int act, float* out,

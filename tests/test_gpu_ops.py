@@ -299,8 +299,13 @@ def test_attention_tcgen05_vs_real_flash_attn(ops, counts, K, H):
                                                   # few row tiles + K split requested: served by narrow (32 / 64 column) output tiles, no partial sums
                                                   (990, 512, 512, 1, True, 8), (3800, 256, 256, 0, True, 4), (3800, 1024, 256, 0, True, 16),
                                                   (990, 512, 96, 0, False, 8), (300, 256, 160, 1, True, 4)])
-def test_gemm_tc_linear_vs_fp64(ops, M, K, N, act, use_res, T):
-    """fp32-faithful: 3xTF32 split keeps the result within ~1e-5 relative of an fp64 reference (cuBLAS SGEMM class)"""
+@pytest.mark.parametrize("narrow", (0, 1))
+def test_gemm_tc_linear_vs_fp64(ops, lib, M, K, N, act, use_res, T, narrow):
+    """fp32-faithful: 3xTF32 split keeps the result within ~1e-5 relative of an fp64 reference (cuBLAS SGEMM class);
+    narrow = the narrow-output-tile alternative to split-K (cdseg_gemm_tc_set_narrow)"""
+    if narrow and T == 1:
+        pytest.skip("the switch only changes launches that ask for a K split")
+    lib.cdseg_gemm_tc_set_narrow(narrow)
     gen = torch.Generator().manual_seed(M + K + N)
     x = torch.randn(M, K, generator=gen); w = torch.randn(N, K, generator=gen) / K ** 0.5
     b = torch.randn(N, generator=gen); r = torch.randn(M, N, generator=gen) if use_res else None
@@ -312,8 +317,11 @@ def test_gemm_tc_linear_vs_fp64(ops, M, K, N, act, use_res, T):
     Bp = ops.gemm_pack_b(w.t().contiguous()[None].to(DEV))
     tiles = -(-M // 128) * -(-N // 128)
     ns = ops.pick_split(tiles, T) if T > 1 else 1
-    out = ops.gemm_tc(x.to(DEV), Bp, N, K // T, bias=b.to(DEV), res=r.to(DEV) if use_res else None, act=act, nsplit=ns, T=T)
-    torch.cuda.synchronize()
+    try:
+        out = ops.gemm_tc(x.to(DEV), Bp, N, K // T, bias=b.to(DEV), res=r.to(DEV) if use_res else None, act=act, nsplit=ns, T=T)
+        torch.cuda.synchronize()
+    finally:
+        lib.cdseg_gemm_tc_set_narrow(0)
     err = (out.cpu().double() - ref).abs().max().item()
     assert err < 2e-5 * max(1.0, ref.abs().max().item()), err
 
