@@ -127,6 +127,8 @@ SIGNATURES = {
     "cdseg_conv_im2col_tc": (_I, [_P, _P, _I, _P, _L, _I, _P, _I, _P, _L, _P]),
     "cdseg_criteria_workspace_bytes": (_Z, [_L, _I]),
     "cdseg_criteria": (_I, [_P, _P, _L, _I, _L, _P, _P, _I, _I, _F, _F, _F, _I, _I, _I, _P, _P, _Z, _P]),
+    "cdseg_criteria_grad": (_I, [_P, _P, _L, _I, _L, _P, _P, _I, _I, _F, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "cdseg_adamw_step": (_I, [_P, _I, _F, _F, _F, _F, _F, _I, _P]),
     "cdseg_q_sample": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P]),
     "cdseg_ddim_step": (_I, [_P, _P, _L, _F, _F, _F, _F, _I, _I, _P, _P]),
     "cdseg_axpy_scale": (_I, [_P, _P, _F, _F, _L, _P]),

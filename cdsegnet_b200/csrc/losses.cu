@@ -81,7 +81,8 @@ __global__ void lovasz_keys_kernel(const float* __restrict__ prob, const int64_t
 constexpr int LV_THREADS = 1024;
 __global__ void __launch_bounds__(LV_THREADS) lovasz_scan_kernel(const float* __restrict__ prob, const int64_t* __restrict__ target,
                                                                   const int32_t* __restrict__ order, const int32_t* __restrict__ cls_count,
-                                                                  int64_t n, int C, int64_t ignore, double* __restrict__ loss) {
+                                                                  int64_t n, int C, int64_t ignore, double* __restrict__ loss,
+                                                                  float* __restrict__ gbuf) {
   __shared__ int s_warp[32];
   __shared__ double s_red[32];
   __shared__ int s_carry;
@@ -127,6 +128,9 @@ __global__ void __launch_bounds__(LV_THREADS) lovasz_scan_kernel(const float* __
       const float jk = 1.0f - (gts - Fk) / (gts + ((float)(k + 1) - Fk));
       const float jp = k > 0 ? 1.0f - (gts - Fp) / (gts + ((float)k - Fp)) : 0.0f;
       part += (double)err * (double)(jk - jp);
+      // d loss_c / d p[i, c]: the Jaccard gradient is a constant of the sort order (autograd sees errors_sorted only, lovasz.py:141-143);
+      // |fg - p| has slope -1 on foreground points and +1 elsewhere
+      if (gbuf) gbuf[(int64_t)ord[k] * C + c] = fg ? -(jk - jp) : (jk - jp);
     }
     __syncthreads();
     if (threadIdx.x == LV_THREADS - 1) s_carry = F;
@@ -187,6 +191,74 @@ __global__ void criteria_finalize_kernel(const double* __restrict__ acc_ce, cons
   out[4] = sqrtf(mse * (ce + lv));
 }
 
+// coef[0] = d loss / d CE-term per valid point = s_seg * w_ce / n_valid, coef[1] = s_seg * w_lov / #present classes,
+// coef[2] = s_mse * w_mse * 2 / #summed elements, with (s_seg, s_mse) = (1, 1) for the EW sum and
+// (MSE / 2L, (CE + Lovasz) / 2L) for the GLS loss L = sqrt(MSE * (CE + Lovasz))  (builder.py:37-49)
+__global__ void criteria_coef_kernel(const double* __restrict__ acc_ce, const double* __restrict__ acc_mse, const int32_t* __restrict__ cls_count,
+                                     int C, float w_mse, float w_ce, float w_lov, int gls, const float* __restrict__ out5,
+                                     float* __restrict__ coef) {
+  if (threadIdx.x || blockIdx.x) return;
+  int present = 0;
+  for (int c = 0; c < C; ++c) present += cls_count[c] > 0;
+  float s_seg = 1.f, s_mse = 1.f;
+  if (gls) { const float L = out5[4]; s_seg = out5[0] / (2.f * L); s_mse = (out5[1] + out5[2]) / (2.f * L); }
+  coef[0] = acc_ce[1] > 0.0 ? s_seg * w_ce / (float)acc_ce[1] : 0.f;
+  coef[1] = present ? s_seg * w_lov / (float)present : 0.f;
+  coef[2] = acc_mse[1] > 0.0 ? s_mse * w_mse * 2.f / (float)acc_mse[1] : 0.f;
+}
+
+// grad[i, j] = coef_ce (p_ij - [j == t_i]) + coef_lov p_ij (G_ij - sum_c G_ic p_ic) on valid points, 0 elsewhere: CE backward plus the
+// Lovasz gradient pulled through the softmax Jacobian; one warp per point
+__global__ void __launch_bounds__(256) seg_grad_kernel(const float* __restrict__ prob, const float* __restrict__ gbuf, const int64_t* __restrict__ target,
+                                                       int64_t n, int C, int64_t ignore, const float* __restrict__ coef, int has_ce, int has_lov,
+                                                       float* __restrict__ grad) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= n) return;
+  const int64_t t = target[i];
+  const bool valid = t != ignore && t >= 0 && t < C;
+  float dot = 0.f;
+  if (valid && has_lov)
+    for (int c = lane; c < C; c += 32) dot += gbuf[i * C + c] * prob[i * C + c];
+  dot = warp_sum(dot);
+  const float a_ce = has_ce ? coef[0] : 0.f, a_lov = has_lov ? coef[1] : 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float g = 0.f;
+    if (valid) {
+      const float p = prob[i * C + c];
+      g = a_ce * (p - (c == t ? 1.f : 0.f));
+      if (has_lov) g += a_lov * p * (gbuf[i * C + c] - dot);
+    }
+    grad[i * C + c] = g;
+  }
+}
+
+__global__ void mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, const int64_t* __restrict__ label, int64_t n, int C,
+                                int64_t ignore, int use_ignore, const float* __restrict__ coef, float* __restrict__ grad) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * C) return;
+  const bool skip = use_ignore && label && label[e / C] == ignore;
+  grad[e] = skip ? 0.f : coef[2] * (pred[e] - tgt[e]);
+}
+
+// AdamW (torch.optim.AdamW, decoupled weight decay) over a table of chunks: entry k = (param, grad, exp_avg, exp_avg_sq, numel) of one
+// chunk (<= 64K elements) of one tensor -- a multi-tensor apply: ONE launch updates every parameter of a group; one CTA per chunk
+struct AdamEntry { float* p; const float* g; float* m; float* v; long long n; };
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamEntry* __restrict__ tab, float lr, float beta1, float beta2, float eps, float wd,
+                                                    float bc1, float bc2_sqrt) {
+  const AdamEntry e = tab[blockIdx.x];
+  const float step = lr / bc1;
+  for (long long i = threadIdx.x; i < e.n; i += blockDim.x) {
+    const float g = e.g[i];
+    float p = e.p[i] * (1.f - lr * wd);
+    const float m = beta1 * e.m[i] + (1.f - beta1) * g;
+    const float v = beta2 * e.v[i] + (1.f - beta2) * g * g;
+    e.m[i] = m; e.v[i] = v;
+    p -= step * (m / (sqrtf(v) / bc2_sqrt + eps));
+    e.p[i] = p;
+  }
+}
+
 // out = a[b] * x0 + c[b] * noise per row (b = batch[row]) : q(x_t | x_0), default.py:216-222
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const int32_t* __restrict__ batch,
                                 const float* __restrict__ sa, const float* __restrict__ sb, int64_t n, int C, float* __restrict__ out) {
@@ -222,16 +294,17 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
 }  // namespace ls
 
 CDSEG_API size_t cdseg_criteria_workspace_bytes(int64_t n, int C) {
-  const size_t head = (((size_t)(4 + C) * 8 + (size_t)C * 4) + 255) & ~(size_t)255;
+  const size_t head = (((size_t)(4 + C) * 8 + (size_t)C * 4 + 16) + 255) & ~(size_t)255;
   const size_t prob = ((size_t)n * C * 4 + 255) & ~(size_t)255;
   const size_t keys = (size_t)n * C * 8, ord = (size_t)n * C * 4;
   return head + prob + keys + 2 * ord + cdseg_argsort_workspace_bytes(C, n) + 256;
 }
 
 // see include/cdseg_b200.h
-CDSEG_API int cdseg_criteria(const float* n_pred, const int64_t* n_target, int64_t n, int C, int64_t ignore, const float* c_pred,
-                             const float* c_target, int Cc, int mse_use_ignore, float w_mse, float w_ce, float w_lov, int has_mse,
-                             int has_ce, int has_lov, float* out5, void* workspace, size_t workspace_bytes, void* stream) {
+static int criteria_impl(const float* n_pred, const int64_t* n_target, int64_t n, int C, int64_t ignore, const float* c_pred,
+                         const float* c_target, int Cc, int mse_use_ignore, float w_mse, float w_ce, float w_lov, int has_mse,
+                         int has_ce, int has_lov, float* out5, int gls, float* grad_n, float* grad_c, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   if (n < 0 || C <= 0 || C > 4096 || !n_pred || !n_target || !out5 || !workspace) return CDSEG_EINVAL;
   if (has_mse && (!c_pred || !c_target || Cc <= 0)) return CDSEG_EINVAL;
   if (workspace_bytes < cdseg_criteria_workspace_bytes(n, C)) return CDSEG_ENOSPC;
@@ -240,17 +313,19 @@ CDSEG_API int cdseg_criteria(const float* n_pred, const int64_t* n_target, int64
   double* acc = (double*)p;                       // [0..1] CE, [2..3] MSE
   double* lov = acc + 4;                          // [C]
   int32_t* cls = (int32_t*)(lov + C);             // [C]
-  const size_t head = (((size_t)(4 + C) * 8 + (size_t)C * 4) + 255) & ~(size_t)255;
+  const size_t head = (((size_t)(4 + C) * 8 + (size_t)C * 4 + 16) + 255) & ~(size_t)255;
   cudaMemsetAsync(p, 0, head, st);
   p += head;
   float* prob = (float*)p; p += ((size_t)n * C * 4 + 255) & ~(size_t)255;
   int64_t* keys = (int64_t*)p; p += (size_t)n * C * 8;
+  float* gbuf = (grad_n && has_lov) ? (float*)keys : nullptr;          // the key rows are dead once the sort has run: reuse them for d loss_c / d p
+  float* coef = (float*)(cls + C);                                      // 3 floats behind the per-class counts (inside the zeroed header)
   int32_t* order = (int32_t*)p; p += (size_t)n * C * 4;
   int32_t* inverse = (int32_t*)p; p += (size_t)n * C * 4;
   const size_t sort_ws = (size_t)((char*)workspace + workspace_bytes - p);
   if (n > 0) {
     const int blocks = (int)(((n + 7) / 8) < 2368 ? ((n + 7) / 8) : 2368);
-    ls::ce_softmax_kernel<<<blocks, 256, 0, st>>>(n_pred, n_target, n, C, ignore, has_lov ? prob : nullptr, acc, cls);
+    ls::ce_softmax_kernel<<<blocks, 256, 0, st>>>(n_pred, n_target, n, C, ignore, (has_lov || grad_n) ? prob : nullptr, acc, cls);
     CDSEG_COUNT_LAUNCH(1);
     if (has_lov) {
       dim3 g((unsigned)cdseg_div_up(n, 256), (unsigned)C);
@@ -258,7 +333,8 @@ CDSEG_API int cdseg_criteria(const float* n_pred, const int64_t* n_target, int64
       CDSEG_COUNT_LAUNCH(1);
       int s = cdseg_argsort_rows(keys, C, n, 31, order, inverse, p, sort_ws, stream);
       if (s != CDSEG_OK) return s;
-      ls::lovasz_scan_kernel<<<C, ls::LV_THREADS, 0, st>>>(prob, n_target, order, cls, n, C, ignore, lov);
+      if (gbuf) cudaMemsetAsync(gbuf, 0, (size_t)n * C * 4, st);         // absent classes and ignored points keep a zero gradient
+      ls::lovasz_scan_kernel<<<C, ls::LV_THREADS, 0, st>>>(prob, n_target, order, cls, n, C, ignore, lov, gbuf);
       CDSEG_COUNT_LAUNCH(1);
     }
     if (has_mse) {
@@ -269,6 +345,47 @@ CDSEG_API int cdseg_criteria(const float* n_pred, const int64_t* n_target, int64
     }
   }
   ls::criteria_finalize_kernel<<<1, 32, 0, st>>>(acc, acc + 2, lov, cls, C, w_mse, w_ce, w_lov, has_mse, has_ce, has_lov, out5);
+  CDSEG_COUNT_LAUNCH(1);
+  if ((grad_n || grad_c) && n > 0) {
+    ls::criteria_coef_kernel<<<1, 32, 0, st>>>(acc, acc + 2, cls, C, w_mse, w_ce, w_lov, gls, out5, coef);
+    CDSEG_COUNT_LAUNCH(1);
+    if (grad_n) {
+      ls::seg_grad_kernel<<<cdseg_div_up(n, 8), 256, 0, st>>>(prob, gbuf, n_target, n, C, ignore, coef, has_ce, has_lov && gbuf, grad_n);
+      CDSEG_COUNT_LAUNCH(1);
+    }
+    if (grad_c && has_mse) {
+      ls::mse_grad_kernel<<<cdseg_div_up(n * Cc, 256), 256, 0, st>>>(c_pred, c_target, n_target, n, Cc, ignore, mse_use_ignore, coef, grad_c);
+      CDSEG_COUNT_LAUNCH(1);
+    }
+  }
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
+
+CDSEG_API int cdseg_criteria(const float* n_pred, const int64_t* n_target, int64_t n, int C, int64_t ignore, const float* c_pred,
+                             const float* c_target, int Cc, int mse_use_ignore, float w_mse, float w_ce, float w_lov, int has_mse,
+                             int has_ce, int has_lov, float* out5, void* workspace, size_t workspace_bytes, void* stream) {
+  return criteria_impl(n_pred, n_target, n, C, ignore, c_pred, c_target, Cc, mse_use_ignore, w_mse, w_ce, w_lov, has_mse, has_ce, has_lov,
+                       out5, 0, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+// forward values + gradients of the selected combination w.r.t. the two network outputs (see include/cdseg_b200.h)
+CDSEG_API int cdseg_criteria_grad(const float* n_pred, const int64_t* n_target, int64_t n, int C, int64_t ignore, const float* c_pred,
+                                  const float* c_target, int Cc, int mse_use_ignore, float w_mse, float w_ce, float w_lov, int has_mse,
+                                  int has_ce, int has_lov, int gls, float* out5, float* grad_n_pred, float* grad_c_pred, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (!grad_n_pred) return CDSEG_EINVAL;
+  return criteria_impl(n_pred, n_target, n, C, ignore, c_pred, c_target, Cc, mse_use_ignore, w_mse, w_ce, w_lov, has_mse, has_ce, has_lov,
+                       out5, gls, grad_n_pred, grad_c_pred, workspace, workspace_bytes, stream);
+}
+
+CDSEG_API int cdseg_adamw_step(const void* table, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                               int step, void* stream) {
+  if (!table || n_chunks < 0 || step < 1) return CDSEG_EINVAL;
+  if (n_chunks == 0) return CDSEG_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  ls::adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>((const ls::AdamEntry*)table, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                               (float)sqrt(bc2));
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;

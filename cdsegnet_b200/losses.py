@@ -74,6 +74,20 @@ class Criteria:
                             c_pred.contiguous() if c_pred is not None else None, c_target.contiguous() if c_target is not None else None,
                             self.mse_use_ignore, self.weights, self.has)
 
+    def value_and_grad(self, point):
+        """(loss, d loss / d n_pred, d loss / d c_pred or None) of the pass `point["loss_mode"]` selects -- what the backward of the
+        network would start from (cdseg_criteria_grad)"""
+        gls = point["loss_mode"] == "train" and self.loss_type == "GLS"
+        if gls and not (self.task_num == 2 and sum(self.has) == 3):
+            raise NotImplementedError("GLS gradients: task_num=2 over [MSELoss, CrossEntropyLoss, LovaszLoss] only")
+        c_pred, c_target = point.get("c_pred"), point.get("c_target")
+        tgt = point["n_target"]
+        tgt = tgt if tgt.dtype is torch.int64 else tgt.long()
+        out, gn, gc = ops.criteria_grad(point["n_pred"].contiguous(), tgt.contiguous(), self.ignore_index,
+                                        c_pred.contiguous() if c_pred is not None else None,
+                                        c_target.contiguous() if c_target is not None else None, self.mse_use_ignore, self.weights, self.has, gls)
+        return (out[4] if gls else out[3]), gn, gc
+
     def __call__(self, point):
         if not self.cfg:
             return point                                            # "loss computation occur in model" (builder.py:25-27)

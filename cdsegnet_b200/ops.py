@@ -457,3 +457,22 @@ def argmax_rows(x):
     out = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
     check(_lib.load().cdseg_argmax_rows(_p(x, torch.float32), x.shape[0], x.shape[1], _p(out), _stream()), "argmax_rows")
     return out
+
+
+def criteria_grad(n_pred, n_target, ignore_index=-1, c_pred=None, c_target=None, mse_use_ignore=True, weights=(1.0, 1.0, 1.0),
+                  has=(True, True, True), gls=False):
+    """criteria() plus d loss / d n_pred and d loss / d c_pred of the EW (gls=False) or GLS combination -> (out5, grad_n, grad_c)"""
+    lib = _lib.load()
+    n, C = n_pred.shape
+    has_mse = bool(has[0]) and c_pred is not None and c_target is not None
+    out = torch.empty(5, dtype=torch.float32, device=n_pred.device)
+    gn = torch.empty_like(n_pred)
+    gc = torch.empty_like(c_pred) if has_mse else None
+    nb = lib.cdseg_criteria_workspace_bytes(n, C)
+    ws = _ws(nb, n_pred.device)
+    check(lib.cdseg_criteria_grad(_p(n_pred, torch.float32), _p(n_target, torch.int64), n, C, int(ignore_index),
+                                  _p(c_pred, torch.float32) if has_mse else None, _p(c_target, torch.float32) if has_mse else None,
+                                  c_pred.shape[1] if has_mse else 0, int(bool(mse_use_ignore)), float(weights[0]), float(weights[1]),
+                                  float(weights[2]), int(has_mse), int(bool(has[1])), int(bool(has[2])), int(bool(gls)), _p(out), _p(gn),
+                                  _p(gc), _p(ws), nb, _stream()), "criteria_grad")
+    return out, gn, gc

@@ -1,0 +1,103 @@
+"""Optimizer side of the training row.
+
+`build_optimizer(cfg, model, param_dicts)` mirrors pointcept/utils/optimizer.py:20-55: parameters whose NAME contains
+`param_dicts[i].keyword` go to group i + 1 with that group's lr / weight_decay (the shipped configs send every "block"
+parameter to lr 0.0002, configs/scannet/CDSegNet.py:143-152), the rest to group 0.  `type="AdamW"` builds `FusedAdamW`, a
+`torch.optim.Optimizer` (so the reference's OneCycleLR scheduler drives its param_groups unchanged) whose `step()` is ONE kernel
+launch per parameter group (cdseg_adamw_step: a multi-tensor apply over a device table of <= 64K-element chunks) instead of
+torch's per-tensor foreach loops.  The network's backward pass is not built yet: gradients must come from elsewhere (tests feed
+synthetic ones and compare against torch.optim.AdamW).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .ops import _stream, check
+
+CHUNK = 1 << 16
+
+
+class _Entry(ctypes.Structure):
+    _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p), ("n", ctypes.c_longlong)]
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._tables = {}
+
+    def _table(self, gi, group):
+        """device table of this group's chunks; rebuilt when a gradient buffer moved (torch may re-allocate .grad)"""
+        ps = [p for p in group["params"] if p.grad is not None]
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        hit = self._tables.get(gi)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        entries = []
+        for p in ps:
+            if p.dtype is not torch.float32 or not p.is_cuda or not p.is_contiguous() or not p.grad.is_contiguous():
+                raise _lib.CdsegError("FusedAdamW needs contiguous fp32 CUDA parameters and gradients")
+            st = self.state[p]
+            if not st:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p)
+                st["exp_avg_sq"] = torch.zeros_like(p)
+            n = p.numel()
+            for off in range(0, n, CHUNK):
+                b = off * 4
+                entries.append(_Entry(p.data_ptr() + b, p.grad.data_ptr() + b, st["exp_avg"].data_ptr() + b, st["exp_avg_sq"].data_ptr() + b,
+                                      min(CHUNK, n - off)))
+        if not entries:
+            self._tables[gi] = (key, None, 0)
+            return None, 0
+        arr = (_Entry * len(entries))(*entries)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        dev = host.to(ps[0].device)
+        self._tables[gi] = (key, dev, len(entries))
+        return dev, len(entries)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        lib = _lib.load()
+        for gi, group in enumerate(self.param_groups):
+            table, n = self._table(gi, group)
+            if not n:
+                continue
+            ps = [p for p in group["params"] if p.grad is not None]
+            for p in ps:
+                self.state[p]["step"] += 1
+            step = self.state[ps[0]]["step"]
+            b1, b2 = group["betas"]
+            check(lib.cdseg_adamw_step(table.data_ptr(), n, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                       float(group["weight_decay"]), int(step), _stream()), "adamw_step")
+        return loss
+
+
+OPTIMIZERS = {"AdamW": FusedAdamW, "SGD": torch.optim.SGD, "Adam": torch.optim.Adam}
+
+
+def build_optimizer(cfg, model, param_dicts=None):
+    """pointcept/utils/optimizer.py:20-55 (cfg: dict with `type`, `lr`, ...; param_dicts: list of dicts with `keyword` and
+    optional lr / momentum / weight_decay)"""
+    cfg = dict(cfg)
+    kind = cfg.pop("type")
+    if param_dicts is None:
+        params = model.parameters()
+    else:
+        params = [dict(params=[], lr=cfg["lr"])]
+        for pd in param_dicts:
+            g = dict(params=[])
+            for k in ("lr", "momentum", "weight_decay"):
+                if k in pd:
+                    g[k] = pd[k]
+            params.append(g)
+        for n, p in model.named_parameters():
+            for i, pd in enumerate(param_dicts):
+                if pd["keyword"] in n:
+                    params[i + 1]["params"].append(p)
+                    break
+            else:
+                params[0]["params"].append(p)
+    return OPTIMIZERS[kind](params, **cfg)

@@ -251,6 +251,21 @@ size_t cdseg_knn_workspace_bytes(int64_t n);
 int cdseg_knn_query(int m, int nsample, const float* xyz, const float* new_xyz, const int32_t* offset, const int32_t* new_offset,
                     int B, int64_t n, int32_t* idx, float* dist2, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training side of the criteria row (the backward of the NETWORK is not built yet) -----------
+ * cdseg_criteria plus the gradients of the selected combination (gls = 0: EW sum / eval; gls = 1: sqrt(MSE * (CE + Lovasz)),
+ * losses/builder.py:37-49) w.r.t. the two network outputs: grad_n_pred fp32 [n, C] (CE backward + the Lovasz gradient pulled
+ * through the softmax; the Jaccard gradient is a constant of the sort order exactly as autograd sees lovasz.py:141-143) and
+ * grad_c_pred fp32 [n, Cc] (NULL when has_mse = 0).  Same workspace size as cdseg_criteria. */
+int cdseg_criteria_grad(const float* n_pred, const int64_t* n_target, int64_t n, int C, int64_t ignore_index, const float* c_pred,
+                        const float* c_target, int Cc, int mse_use_ignore, float w_mse, float w_ce, float w_lov, int has_mse,
+                        int has_ce, int has_lov, int gls, float* out5, float* grad_n_pred, float* grad_c_pred, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* one AdamW step (torch.optim.AdamW semantics, the optimizer of configs/scannet/CDSegNet.py:143 built by utils/optimizer.py:20-55)
+ * over n_chunks table entries {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64 numel} (device memory,
+ * one entry per <= 64K-element chunk of a tensor): one launch per parameter group; step counts from 1 */
+int cdseg_adamw_step(const void* table, int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

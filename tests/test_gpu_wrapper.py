@@ -131,3 +131,62 @@ def test_wrapper_forward_criteria_vs_reference():
     seg.train()
     with pytest.raises(NotImplementedError):
         seg(_inputs())
+
+
+# ------------------------------------------------------------------ training side: criteria gradients + optimizer (§8(f) rank 2)
+@pytest.mark.parametrize("i", range(4))
+@pytest.mark.parametrize("gls", (False, True))
+def test_criteria_gradients_vs_autograd(ops, i, gls):
+    """d loss / d logits and d loss / d c_pred of the EW sum and of the GLS loss == torch autograd through the oracle's restatement of the
+    reference criteria (fp32; Lovasz gradient = Jaccard gradient at the sorted position, pulled through the softmax)"""
+    g = lambda k: torch.from_numpy(Z[f"loss{i}_{k}"])
+    logits, cp = g("logits").clone().requires_grad_(True), g("c_pred").clone().requires_grad_(True)
+    loss, _ = W.criteria(dict(n_pred=logits, n_target=g("labels"), c_pred=cp, c_target=g("c_target"), loss_mode="train"), "GLS" if gls else "EW", 2)
+    loss.backward()
+    out, gn, gc = ops.criteria_grad(g("logits").to(DEV), g("labels").to(DEV), -1, g("c_pred").to(DEV), g("c_target").to(DEV), gls=gls)
+    assert abs(float(out[4 if gls else 3]) - float(loss.detach())) < 2e-5 * abs(float(loss.detach()))
+    for got, ref in ((gn, logits.grad), (gc, cp.grad)):
+        scale = float(ref.abs().max())
+        assert float((got.cpu() - ref).abs().max()) < 1e-4 * scale + 1e-9, (float((got.cpu() - ref).abs().max()), scale)
+
+
+def test_criteria_value_and_grad_api(ops):
+    from cdsegnet_b200.losses import build_criteria
+    crit = build_criteria(J["wrapper"]["criteria"], "GLS", 2)
+    g = lambda k: torch.from_numpy(Z[f"loss0_{k}"]).to(DEV)
+    point = dict(n_pred=g("logits"), n_target=g("labels"), c_pred=g("c_pred"), c_target=g("c_target"), loss_mode="train")
+    loss, gn, gc = crit.value_and_grad(point)
+    assert abs(float(loss) - float(Z["loss0_GLS_train"])) < 2e-5 * float(loss) and gn.shape == point["n_pred"].shape and gc.shape == point["c_pred"].shape
+    loss_e, gn_e, _ = crit.value_and_grad(dict(point, loss_mode="eval"))
+    assert abs(float(loss_e) - float(Z["loss0_GLS_eval"])) < 2e-5 * float(loss_e)
+    assert float(gn[g("labels") == -1].abs().max()) == 0.0                    # ignored points carry no gradient
+
+
+def test_fused_adamw_vs_torch_and_param_groups():
+    """build_optimizer: keyword groups like utils/optimizer.py:20-55; FusedAdamW (one launch per group) == torch.optim.AdamW over several
+    steps with changing lr / betas (what OneCycleLR does to the groups)"""
+    import cdsegnet_b200 as cb
+    from cdsegnet_b200.optim import build_optimizer, FusedAdamW
+    torch.manual_seed(0)
+    m = cb.PointTransformerV3(**dict(J["cfg"])).to(DEV)
+    ref = {n: p.detach().cpu().clone().requires_grad_(True) for n, p in m.named_parameters()}
+    opt = build_optimizer(dict(type="AdamW", lr=0.002, weight_decay=0.05), m, [dict(keyword="block", lr=0.0002)])
+    assert isinstance(opt, FusedAdamW) and len(opt.param_groups) == 2
+    names1 = [n for n, _ in m.named_parameters() if "block" in n]
+    assert len(opt.param_groups[1]["params"]) == len(names1) > 0 and opt.param_groups[1]["lr"] == 0.0002 and opt.param_groups[0]["lr"] == 0.002
+    topt = torch.optim.AdamW([dict(params=[ref[n] for n, _ in m.named_parameters() if "block" not in n], lr=0.002),
+                              dict(params=[ref[n] for n in names1], lr=0.0002)], lr=0.002, weight_decay=0.05)
+    gen = torch.Generator().manual_seed(1)
+    for it in range(4):
+        for n, p in m.named_parameters():
+            gr = torch.randn(p.shape, generator=gen) * 0.1
+            p.grad = gr.to(DEV)
+            ref[n].grad = gr.clone()
+        for o in (opt, topt):
+            for gi, grp in enumerate(o.param_groups):                                  # a scheduler moving lr and beta1 between steps
+                grp["lr"] = (0.002 if gi == 0 else 0.0002) * (1 + 0.3 * it)
+                grp["betas"] = (0.9 - 0.01 * it, 0.999)
+        opt.step(); topt.step()
+    torch.cuda.synchronize()
+    worst = max(float((p.detach().cpu() - ref[n]).abs().max()) for n, p in m.named_parameters())
+    assert worst < 2e-6, worst
