@@ -99,6 +99,7 @@ SIGNATURES = {
     "cdseg_attn_pack_f16": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "cdseg_attn_pack_f32": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "cdseg_attn_pack_f16v": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "cdseg_attn_set_poly": (None, [_I]),
     "cdseg_attn_tc2": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
     "cdseg_attn_tc_smem_bytes": (_Z, [_I]),
     "cdseg_attn_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),

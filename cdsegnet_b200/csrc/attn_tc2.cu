@@ -110,6 +110,22 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-4 polynomial
+// (|rel err| <= 3.1e-6, far below the 4.9e-4 fp16 rounding of P), 2^n by adding n to the exponent field.  The softmax is bound by the 16
+// MUFU.EX2 per clock and SM (profiles/r01d_ncu_attn_tc2_kernel.md: XU pipe 65 %, issue slots 42 %), so moving a fraction of the
+// exponentials onto the idle FMA slots raises the ceiling (the trick FlashAttention-4 uses on the same hardware).
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -120.f);
+  const float t = x + 12582912.f;                     // 1.5 * 2^23: the low mantissa bits of t now hold round(x)
+  const float f = x - (t - 12582912.f);
+  float p = 0.0096004f;                               // relative-error least-squares fit of 2^f on Chebyshev nodes: max 3.1e-6 in fp32
+  p = fmaf(p, f, 0.05591689f);
+  p = fmaf(p, f, 0.24023718f);
+  p = fmaf(p, f, 0.69312199f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);              // M128 N64, A,B K-major
 constexpr uint32_t IDESC_O = (1u << 4) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);          // M128 N32, B MN-major
 
@@ -118,7 +134,7 @@ struct Bars {
   uint32_t tmem_slot, pad;
 };
 
-template <int OCC>
+template <int OCC, int POLY>       // POLY of every 8 exponentials go to the FMA pipe (0 = all on MUFU)
 __global__ void __launch_bounds__(NTHREADS, OCC)
 attn_tc2_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, const __half* __restrict__ Vp,
                 const int32_t* __restrict__ patch_len, const int32_t* __restrict__ slot_dst, int H, int T, int Kp, float sl2,
@@ -252,8 +268,9 @@ attn_tc2_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
         uint32_t pk[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float p0 = ex2(fmaf(__uint_as_float(s[kg * 8 + 2 * j]), sl2, -msc));
-          const float p1 = ex2(fmaf(__uint_as_float(s[kg * 8 + 2 * j + 1]), sl2, -msc));
+          const float x0 = fmaf(__uint_as_float(s[kg * 8 + 2 * j]), sl2, -msc), x1 = fmaf(__uint_as_float(s[kg * 8 + 2 * j + 1]), sl2, -msc);
+          const float p0 = (2 * j < POLY) ? ex2_fma(x0) : ex2(x0);
+          const float p1 = (2 * j + 1 < POLY) ? ex2_fma(x1) : ex2(x1);
           __half2 hh = __floats2half2_rn(p0, p1);
           pk[j] = *reinterpret_cast<uint32_t*>(&hh);
         }
@@ -287,6 +304,10 @@ attn_tc2_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
 
 // Q, K: fp16 packed [H][T][Kp][16]; V: fp16 packed 32 wide [H][T][Kp][32] with the ones column (cdseg_attn_pack_f16v, v_ones=1).
 // out: fp32 [n, out_ld]; head h -> columns h*16 .. h*16+15 of row slot_dst[slot].
+// exponentials per group of 8 computed on the FMA pipe instead of MUFU (0..3); env CDSEG_ATTN_POLY or cdseg_attn_set_poly
+static int g_attn_poly = [] { const char* e = getenv("CDSEG_ATTN_POLY"); return e ? atoi(e) : 0; }();
+CDSEG_API void cdseg_attn_set_poly(int per8) { g_attn_poly = per8 < 0 ? 0 : (per8 > 3 ? 3 : per8); }
+
 CDSEG_API int cdseg_attn_tc2(const void* Q, const void* K, const void* V32, const int32_t* patch_len,
                              const int32_t* slot_dst, int H, int T, int Kp, float scale, float* out, int64_t out_ld,
                              void* stream) {
@@ -297,19 +318,26 @@ CDSEG_API int cdseg_attn_tc2(const void* Q, const void* K, const void* V32, cons
   if (!occ) {
     const char* e = getenv("CDSEG_ATTN_OCC");                    // 3 (113 regs, no spill) or 4 (96 regs, 84 B spill) CTAs per SM
     occ = (e && e[0] == '4') ? 4 : 3;                            // measured equal (100.4 vs 102.4 us at stage 0): default 3
-    cudaError_t e1 = cudaFuncSetAttribute(tc2::attn_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e2 = cudaFuncSetAttribute(tc2::attn_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e1 = cudaFuncSetAttribute(tc2::attn_tc2_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e2 = cudaFuncSetAttribute(tc2::attn_tc2_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e3 = cudaFuncSetAttribute(tc2::attn_tc2_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e4 = cudaFuncSetAttribute(tc2::attn_tc2_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e5 = cudaFuncSetAttribute(tc2::attn_tc2_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e1 != cudaSuccess) return (int)e1;
     if (e2 != cudaSuccess) return (int)e2;
+    if (e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) return (int)(e3 != cudaSuccess ? e3 : e4 != cudaSuccess ? e4 : e5);
   }
   dim3 g(Kp / 128, T, H);
   const float sl2 = scale * 1.4426950408889634f;
-  if (occ == 3)
-    tc2::attn_tc2_kernel<3><<<g, tc2::NTHREADS, smem, (cudaStream_t)stream>>>((const __half*)Q, (const __half*)K, (const __half*)V32,
-                                                                            patch_len, slot_dst, H, T, Kp, sl2, out, out_ld);
-  else
-    tc2::attn_tc2_kernel<4><<<g, tc2::NTHREADS, smem, (cudaStream_t)stream>>>((const __half*)Q, (const __half*)K, (const __half*)V32,
-                                                                            patch_len, slot_dst, H, T, Kp, sl2, out, out_ld);
+#define CDSEG_ATTN_LAUNCH(O, P)                                                                                              \
+  tc2::attn_tc2_kernel<O, P><<<g, tc2::NTHREADS, smem, (cudaStream_t)stream>>>((const __half*)Q, (const __half*)K, (const __half*)V32, \
+                                                                               patch_len, slot_dst, H, T, Kp, sl2, out, out_ld)
+  if (occ == 4) CDSEG_ATTN_LAUNCH(4, 0);
+  else if (g_attn_poly == 1) CDSEG_ATTN_LAUNCH(3, 1);
+  else if (g_attn_poly == 2) CDSEG_ATTN_LAUNCH(3, 2);
+  else if (g_attn_poly == 3) CDSEG_ATTN_LAUNCH(3, 3);
+  else CDSEG_ATTN_LAUNCH(3, 0);
+#undef CDSEG_ATTN_LAUNCH
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;

@@ -97,6 +97,8 @@ int cdseg_attn_tc(const void* Q, const void* K, const void* V, const int32_t* pa
  * column (cdseg_attn_pack_f16v with v_ones = 1: the LAST packed tensor gets [v(16) | 1 | 0 x 15] per key) */
 int cdseg_attn_pack_f16v(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src, int H,
                          int T, int Kp, void* dst0, void* dst1, void* dst2, int v_ones, void* stream);
+/* how many of every 8 softmax exponentials cdseg_attn_tc2 evaluates with the FMA-pipe polynomial instead of MUFU.EX2 (0..3) */
+void cdseg_attn_set_poly(int per8);
 int cdseg_attn_tc2(const void* Q, const void* K, const void* V32, const int32_t* patch_len, const int32_t* slot_dst,
                    int H, int T, int Kp, float scale, float* out, int64_t out_ld, void* stream);
 /* exact fp32 SIMT kernel (dense-branch numerics, ptv3.py:264-280) */

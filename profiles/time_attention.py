@@ -26,6 +26,33 @@ for H in (2, 4):
         print(f"H={H} kernel={'attn_tc2' if v2 else 'attn_tc '} OCC={os.environ.get('CDSEG_ATTN_OCC','4')}: {ms*1e3:7.1f} us  "
               f"{4.0*pm['pairs']*C/ms/1e9:7.1f} TFLOP/s  {ex/ms/1e9:6.2f} Texp/s ({100*ex/ms/1e9/4.653:.0f}% of MUFU peak)")
 
+# ---- FMA-pipe exponentials: POLY of every 8 exponentials by polynomial instead of MUFU.EX2 (cdseg_attn_set_poly)
+from cdsegnet_b200 import _lib
+lib = _lib.load()
+for H in (2, 4):
+    C = 16 * H
+    order = torch.randperm(n, device=dev).int()
+    pm = ops.patch_maps(order, np.array([n]), K)
+    qkv = torch.randn(n, 3 * C, device=dev)
+    ops.ATTN_V2 = True
+    q, k, v = ops.attn_pack(qkv, 0, C, 3, pm, H)
+    lib.cdseg_attn_set_poly(0)
+    base = ops.attn(q, k, v, pm, H, 0.25, n).clone()
+    for poly in (0, 1, 2, 3):
+        lib.cdseg_attn_set_poly(poly)
+        ts = []
+        for i in range(12):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); o = ops.attn(q, k, v, pm, H, 0.25, n); e1.record(); torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts))
+        ex = pm["pairs"] * H
+        print(f"H={H} poly={poly}/8: {ms*1e3:7.1f} us  {4.0*pm['pairs']*C/ms/1e9:7.1f} TFLOP/s  {ex/ms/1e9:6.2f} Texp/s ({100*ex/ms/1e9/4.653:.0f}% of the MUFU-only peak)"
+              f"  max|o - o_poly0| = {(o - base).abs().max().item():.2e}")
+lib.cdseg_attn_set_poly(0)
+
 # ---- upstream-kernel comparator: flash_attn 2.8.3's varlen kernel on the same stage-0 problem, alone and inside the
 # reference's own sequence qkv[order] -> .half() -> flash_attn_varlen_qkvpacked_func -> feat[inverse] (ptv3.py:258-290)
 try:
