@@ -203,7 +203,8 @@ def run_cuda(args):
     random_weights(seg)
     seg = seg.to(dev).eval()
 
-    sc = make_scene(seed=rank)
+    sc = make_scene(seed=0)           # the SAME scene on every rank: weak scaling keeps the per-GPU work identical (different seeds give
+                                      # 120k-point scenes whose step times differ by up to 8 %, profiles/r01f_bench_4gpu.json)
     n = len(sc["coord"])
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in sc.items()}
     host["grid_coord"] = host["grid_coord"].int().pin_memory()
@@ -341,7 +342,7 @@ def run_cuda(args):
             "config": {"workload": "ScanNet-shaped scene 120k unique voxels @0.02 m, full CDSegNet (CN+NN+TransferModule, 101.4M params), "
                                    "single-step inference forward, patch 1024, 1 scene per GPU",
                        "points_per_step_per_gpu": n, "l2": "flushed (256 MiB write) between timed iterations",
-                       "parallelism": f"scene-per-GPU x{world}, no collective"},
+                       "parallelism": f"scene-per-GPU x{world} (same synthetic scene on every rank), no collective"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "points/s",
                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) + n * 6 * 4),
