@@ -86,6 +86,8 @@ SIGNATURES = {
     "cdseg_debug_encode_host": (_I, [_P, _P, _L, _I, _I, _P]),
     "cdseg_argsort_workspace_bytes": (_Z, [_I, _L]),
     "cdseg_argsort_rows": (_I, [_P, _I, _L, _I, _P, _P, _P, _Z, _P]),
+    "cdseg_gather_rows": (_I, [_P, _P, _L, _I, _P, _P]),
+    "cdseg_renumber": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _P]),
     "cdseg_patch_count": (_I, [ctypes.POINTER(_L), _I, _I, ctypes.POINTER(_I)]),
     "cdseg_patch_maps": (_I, [_P, ctypes.POINTER(_L), _I, _I, _I, _P, _P, _P, _P, _P]),
     "cdseg_pool_plan_workspace_bytes": (_Z, [_I, _L]),

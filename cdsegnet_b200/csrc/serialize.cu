@@ -402,3 +402,60 @@ CDSEG_API int cdseg_patch_maps(const int32_t* order, const int64_t* scene_count,
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;
 }
+
+// ---------------------------------------------------------------------------------
+// curve-order renumbering of level 0 (structure.py::Plan) and plain row gathers: the "patch gather/scatter" plumbing around the
+// network -- feat[perm], coord[perm], logits[inv_perm] -- as coalesced kernels instead of a dozen advanced-indexing launches.
+// ---------------------------------------------------------------------------------
+// dst[i, :] = src[idx[i], :] for rows of `words` 32-bit words (a thread moves one word; consecutive threads walk a row, then the next row)
+__global__ void gather_rows_kernel(const uint32_t* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, int words,
+                                   uint32_t* __restrict__ dst) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n * words) return;
+  const int64_t i = e / words;
+  const int w = (int)(e - i * words);
+  dst[e] = src[(int64_t)idx[i] * words + w];
+}
+
+CDSEG_API int cdseg_gather_rows(const void* src, const int32_t* idx, int64_t n, int row_bytes, void* dst, void* stream) {
+  if (n < 0 || row_bytes <= 0 || (row_bytes & 3) || !src || !idx || !dst) return CDSEG_EINVAL;
+  if (n == 0) return CDSEG_OK;
+  const int words = row_bytes / 4;
+  gather_rows_kernel<<<cdseg_div_up(n * words, 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, idx, n, words, (uint32_t*)dst);
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
+
+// internal point r = original point perm[r]:  i_grid[r] = grid[perm[r]], i_batch[r] = batch[perm[r]], and for every curve c
+// i_code[c][r] = code[c][perm[r]], i_inverse[c][r] = inverse[c][perm[r]], i_order[c][j] = inv_perm[order[c][j]]
+__global__ void renumber_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ inv_perm, const int32_t* __restrict__ grid,
+                                const int32_t* __restrict__ batch, const int64_t* __restrict__ code, const int32_t* __restrict__ order,
+                                const int32_t* __restrict__ inverse, int k, int64_t N, int32_t* __restrict__ i_grid,
+                                int32_t* __restrict__ i_batch, int64_t* __restrict__ i_code, int32_t* __restrict__ i_order,
+                                int32_t* __restrict__ i_inverse) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const int64_t p = perm[r];
+  i_grid[3 * r] = grid[3 * p]; i_grid[3 * r + 1] = grid[3 * p + 1]; i_grid[3 * r + 2] = grid[3 * p + 2];
+  i_batch[r] = batch[p];
+  for (int c = 0; c < k; ++c) {
+    i_code[c * N + r] = code[c * N + p];
+    i_inverse[c * N + r] = inverse[c * N + p];
+    i_order[c * N + r] = inv_perm[order[c * N + r]];
+  }
+}
+
+CDSEG_API int cdseg_renumber(const int32_t* perm, const int32_t* inv_perm, const int32_t* grid, const int32_t* batch, const int64_t* code,
+                             const int32_t* order, const int32_t* inverse, int k, int64_t N, int32_t* i_grid, int32_t* i_batch,
+                             int64_t* i_code, int32_t* i_order, int32_t* i_inverse, void* stream) {
+  if (k <= 0 || N < 0 || !perm || !inv_perm || !grid || !batch || !code || !order || !inverse || !i_grid || !i_batch || !i_code || !i_order ||
+      !i_inverse)
+    return CDSEG_EINVAL;
+  if (N == 0) return CDSEG_OK;
+  renumber_kernel<<<cdseg_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(perm, inv_perm, grid, batch, code, order, inverse, k, N, i_grid,
+                                                                          i_batch, i_code, i_order, i_inverse);
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}

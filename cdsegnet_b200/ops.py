@@ -99,6 +99,25 @@ def argsort_rows(codes, nbits):
     return order, inverse
 
 
+def gather_rows(src, idx):
+    """src[idx] for a contiguous 2-D (or 1-D) tensor with 4-byte-multiple rows and an int32 index vector"""
+    n = idx.shape[0]
+    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    row_bytes = src.element_size() * (src[0].numel() if src.dim() > 1 else 1)
+    check(_lib.load().cdseg_gather_rows(_p(src), _p(idx, torch.int32), n, row_bytes, _p(out), _stream()), "gather_rows")
+    return out
+
+
+def renumber(perm, inv_perm, grid, batch, code, order, inverse):
+    """level-0 tables in curve-order numbering (see include/cdseg_b200.h) -> (i_grid, i_batch, i_code, i_order, i_inverse)"""
+    k, N = code.shape
+    outs = (torch.empty_like(grid), torch.empty_like(batch), torch.empty_like(code), torch.empty_like(order), torch.empty_like(inverse))
+    check(_lib.load().cdseg_renumber(_p(perm, torch.int32), _p(inv_perm, torch.int32), _p(grid, torch.int32), _p(batch, torch.int32),
+                                     _p(code, torch.int64), _p(order, torch.int32), _p(inverse, torch.int32), k, N, *[_p(o) for o in outs],
+                                     _stream()), "renumber")
+    return outs
+
+
 def patch_maps(order_row, scene_count, K):
     """order_row int32 [n] (one curve).  Returns dict(slot_src, slot_dst, point_slot, patch_len, T, Kp)."""
     lib = _lib.load()

@@ -159,11 +159,7 @@ class Plan:
         # point perm[r].  Every level-0 kernel (conv tiles, patch gathers, LayerNorm rows) then walks
         # memory in space-filling-curve order; inputs are gathered once and the logits scattered back.
         perm, inv_perm = order[0], inverse[0]
-        pl = perm.long()
-        i_grid, i_batch = grid[pl].contiguous(), batch[pl].contiguous()
-        i_code = code[:, pl].contiguous()
-        i_order = inv_perm[order.long()].contiguous()          # original ids -> internal ids
-        i_inverse = inverse[:, pl].contiguous()
+        i_grid, i_batch, i_code, i_order, i_inverse = ops.renumber(perm, inv_perm, grid, batch, code, order, inverse)
 
         def level0():
             L = Level()

@@ -45,6 +45,13 @@ int cdseg_argsort_rows(const int64_t* codes, int k, int64_t N, int nbits, int32_
 /* ---- patch maps: replaces SerializedAttention.get_padding_and_inverse, ptv3.py:188-244 ----------------- */
 /* scene_count: host int64[B] points per scene (B <= 64).  K = patch size, Kp = round_up(K,128) slots per patch.
  * slot_src/slot_dst: int32[T*Kp], point_slot: int32[N], patch_len: int32[T]  (T from cdseg_patch_count) */
+/* dst[i, :] = src[idx[i], :] for rows of row_bytes bytes (multiple of 4): feat[perm], coord[perm], logits[inv_perm] around the network */
+int cdseg_gather_rows(const void* src, const int32_t* idx, int64_t n, int row_bytes, void* dst, void* stream);
+/* level-0 renumbering along the first curve (internal point r = original point perm[r], perm = order[0], inv_perm = inverse[0]):
+ * grid / batch / code / inverse gathered by perm, order composed with inv_perm; code int64 [k,N], order / inverse int32 [k,N] */
+int cdseg_renumber(const int32_t* perm, const int32_t* inv_perm, const int32_t* grid, const int32_t* batch, const int64_t* code,
+                   const int32_t* order, const int32_t* inverse, int k, int64_t N, int32_t* i_grid, int32_t* i_batch,
+                   int64_t* i_code, int32_t* i_order, int32_t* i_inverse, void* stream);
 int cdseg_patch_count(const int64_t* scene_count, int B, int K, int* T_out);
 int cdseg_patch_maps(const int32_t* order, const int64_t* scene_count, int B, int K, int Kp, int32_t* slot_src,
                      int32_t* slot_dst, int32_t* point_slot, int32_t* patch_len, void* stream);
