@@ -142,8 +142,9 @@ def patch_maps(order_row, scene_count, K):
 
 
 # ---------------------------------------------------------------- pooling
-def pool_plan(code, order, n_dev, n_host, c0, pooling_depth, grid, batch, B, cap_child):
-    """One sync-free pooling level.  code/order: [k, ld].  Returns the child arrays (capacity cap_child)."""
+def pool_plan(code, order, n_dev, n_host, c0, pooling_depth, grid, batch, B, cap_child, m_dev=None, offset=None):
+    """One sync-free pooling level.  code/order: [k, ld].  Returns the child arrays (capacity cap_child).
+    m_dev int32 [1] / offset int64 [B]: optional pre-zeroed outputs (the Plan hands out slices of one buffer per forward)."""
     lib = _lib.load()
     k, ld = code.shape
     dev = code.device
@@ -157,8 +158,8 @@ def pool_plan(code, order, n_dev, n_host, c0, pooling_depth, grid, batch, B, cap
         inverse=torch.empty((k, cap_child), dtype=torch.int32, device=dev),
         grid=torch.empty((cap_child, 3), dtype=torch.int32, device=dev),
         batch=torch.empty(cap_child, dtype=torch.int32, device=dev),
-        m_dev=torch.zeros(1, dtype=torch.int32, device=dev),
-        offset=torch.zeros(B, dtype=torch.int64, device=dev),
+        m_dev=m_dev if m_dev is not None else torch.zeros(1, dtype=torch.int32, device=dev),
+        offset=offset if offset is not None else torch.zeros(B, dtype=torch.int64, device=dev),
     )
     nb = lib.cdseg_pool_plan_workspace_bytes(k, ld)
     ws = _ws(nb, dev)

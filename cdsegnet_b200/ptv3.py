@@ -30,6 +30,9 @@ class Point(dict):
     """dict with attribute access standing in for pointcept's addict-based Point
     (pointcept/models/utils/structure.py:14).  ``_level`` links to the GPU-side structure."""
 
+    _LAZY = {"batch": lambda L: L.batch.long(), "serialized_code": lambda L: L.serialized("code"),
+             "serialized_order": lambda L: L.serialized("order"), "serialized_inverse": lambda L: L.serialized("inverse")}
+
     def __getattr__(self, k):
         try:
             return self[k]
@@ -38,6 +41,19 @@ class Point(dict):
 
     def __setattr__(self, k, v):
         self[k] = v
+
+    def __missing__(self, k):
+        """reference-shaped int64 views of an exported point (`batch`, `serialized_code/order/inverse`, structure.py:47-102):
+        nobody on the inference path reads them, so they are materialised on first access instead of on every forward"""
+        L = dict.get(self, "_export_level")
+        if L is not None and k in self._LAZY:
+            v = self._LAZY[k](L)
+            self[k] = v
+            return v
+        raise KeyError(k)
+
+    def __contains__(self, k):
+        return dict.__contains__(self, k) or (k in self._LAZY and dict.get(self, "_export_level") is not None)
 
 
 class Seq(nn.Module):
@@ -681,10 +697,7 @@ class PointTransformerV3(nn.Module):
         L = p["_level"]
         p["feat"] = ops.gather_rows(p["feat"].contiguous(), L.inv_perm)
         p["coord"] = ops.gather_rows(p["coord"].contiguous(), L.inv_perm)
-        p["batch"] = L.batch.long()                  # batch ids are sorted in both numberings
         p.pop("conv_in", None)
         p["serialized_depth"] = L.depth
-        p["serialized_code"] = L.serialized("code")
-        p["serialized_order"] = L.serialized("order")
-        p["serialized_inverse"] = L.serialized("inverse")
+        p["_export_level"] = L                       # `batch` (sorted in both numberings) and `serialized_*` resolve lazily (Point.__missing__)
         return p

@@ -47,6 +47,7 @@ class DefaultSegmentorV2(nn.Module):
         self.dm_min_snr = dm_min_snr
         self.c_in_channels = c_in_channels
         self._dev_sched = {}
+        self._t_cache = {}
         if self.dm:
             self.eps = 1e-6
             Beta, Alpha, Alpha_bar, Sigma, SNR = self.get_diffusion_hyperparams(noise_schedule=noise_schedule, T=T,
@@ -141,8 +142,13 @@ class DefaultSegmentorV2(nn.Module):
     def _t_emb(self, t, input_dict):
         """one row per scene (the reference builds N identical rows per scene, default.py:400-403)"""
         B = input_dict["offset"].numel()
-        ts = t * torch.ones((B, 1), dtype=torch.int64, device=input_dict["feat"].device)
-        return calc_t_emb(ts, self.T_dim)
+        key = (int(t), B, input_dict["feat"].device)
+        if key not in self._t_cache:                          # a constant of (t, B): seven tiny launches per forward otherwise
+            if len(self._t_cache) > 64:
+                self._t_cache.clear()
+            ts = t * torch.ones((B, 1), dtype=torch.int64, device=input_dict["feat"].device)
+            self._t_cache[key] = calc_t_emb(ts, self.T_dim)
+        return self._t_cache[key]
 
     def _result(self, logits, input_dict, eval):
         if not eval:

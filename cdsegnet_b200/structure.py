@@ -183,6 +183,14 @@ class Plan:
         n0.rowmap = _draw(k, perm_fn) if shuffle_orders else list(range(k))
         self.n_levels = [n0]
 
+        n_pool = len(n_strides) + (len(c_strides) if c_strides is not None else 0)
+        n_flag = extra_flags.numel() if extra_flags is not None else 0
+        # every pooled level's point count (int32) and per-scene offsets (int64) land in two small buffers: one zero fill and
+        # one device-to-host copy each per forward instead of a fill / cast / cat per level
+        cnt_buf = torch.zeros(max(n_pool, 1), dtype=torch.int32, device=dev)
+        off_buf = torch.zeros((max(n_pool, 1), B), dtype=torch.int64, device=dev)
+        slot = [0]
+
         def pool(levels, stride):
             par = levels[-1]
             pd = (int(np.ceil(stride)) - 1).bit_length()
@@ -191,8 +199,11 @@ class Plan:
             ch = Level()
             ch.parent, ch.c0, ch.pooling_depth = par, par.rowmap[0], pd
             ch.cap, ch.B, ch.depth = par.cap, B, par.depth - pd
+            i = slot[0]
+            slot[0] += 1
             out = ops.pool_plan(par.code, par.order, par.m_dev, par.n if par.m_dev is None else 0, ch.c0, pd, par.grid,
-                                par.batch, B, ch.cap)
+                                par.batch, B, ch.cap, cnt_buf[i:i + 1], off_buf[i])
+            ch.slot = i
             ch.cluster, ch.idx_ptr, ch.head = out["cluster"], out["idx_ptr"], out["head"]
             ch.code, ch.order, ch.inverse = out["code"], out["order"], out["inverse"]
             ch.grid, ch.batch, ch.m_dev, ch.offset_dev = out["grid"], out["batch"], out["m_dev"], out["offset"]
@@ -210,14 +221,12 @@ class Plan:
 
         # --- sync #2: pooled sizes + offsets (+ caller flags) ------------------------------
         pooled = [L for L in (self.c_levels or [])[1:] + self.n_levels[1:]]
-        parts = [L.m_dev.to(torch.int64) for L in pooled] + [L.offset_dev for L in pooled]
-        if extra_flags is not None:
-            parts.append(extra_flags.to(torch.int64).reshape(-1))
         self.flags = None
-        if parts:
-            host = torch.cat(parts).cpu().numpy()
-            for i, L in enumerate(pooled):
-                L.n = int(host[i])
-                L.offset_host = host[len(pooled) + i * B: len(pooled) + (i + 1) * B].astype(np.int64)
+        if pooled or extra_flags is not None:
+            cnt_host = cnt_buf.cpu().numpy()
+            off_host = off_buf.cpu().numpy()
+            for L in pooled:
+                L.n = int(cnt_host[L.slot])
+                L.offset_host = off_host[L.slot].astype(np.int64)
             if extra_flags is not None:
-                self.flags = host[len(pooled) * (B + 1):]
+                self.flags = extra_flags.cpu().numpy().astype(np.int64).reshape(-1)
