@@ -107,6 +107,7 @@ SIGNATURES = {
     "cdseg_attn_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
     "cdseg_attn_exact": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
     "cdseg_add_layernorm": (_I, [_P, _P, _P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),
+    "cdseg_reduce_ln": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),
     "cdseg_scale_shift_act": (_I, [_P, _P, _P, _I, _L, _I, _P, _P]),
     "cdseg_small_linear": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "cdseg_rows_uniform": (_I, [_P, _P, _P, _L, _I, _P, _P]),

@@ -33,6 +33,19 @@ static int run_linear(const float* x, int64_t n, int K, int N, const float* Bp, 
   return cdseg_gemm_tc(x, K, nullptr, T, nullptr, Bp, n, N, K / T, bias, res, N, act, out, N, ns, ws, ws_bytes, stream);
 }
 
+// a Linear whose split-K partials (if any) are left for cdseg_reduce_ln: returns the status, *ns_out = number of partials in ws
+// (1: `out` holds the finished result, bias included)
+static int run_linear_raw(const float* x, int64_t n, int K, int N, const float* Bp, const float* bias, float* out, void* ws,
+                          size_t ws_bytes, void* stream, int* ns_out) {
+  const int64_t tiles = ((n + 127) / 128) * ((N + 127) / 128);
+  int T = 1;
+  if (tiles < 120 && K >= 256) T = K / 64;
+  const int ns = pick_split(tiles, T);
+  *ns_out = ns;
+  if (ns > 1 && cdseg_gemm_tc_workspace_bytes(n, N, ns) > ws_bytes) return CDSEG_ENOSPC;
+  return cdseg_gemm_tc(x, K, nullptr, T, nullptr, Bp, n, N, K / T, bias, nullptr, N, 0, ns > 1 ? nullptr : out, N, ns, ws, ws_bytes, stream);
+}
+
 CDSEG_API size_t cdseg_block_scratch_bytes(int64_t n, int C, int H, int T, int Kp, int B) {
   const size_t row = align_up((size_t)n * C * 4);
   size_t s = 0;
@@ -93,15 +106,23 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
                       ns, ws, ws_bytes, stream));
     if (a->ev[5]) cudaEventRecord((cudaEvent_t)a->ev[5], (cudaStream_t)stream);
   }
-  RUN(run_linear(y1, n, C, C, a->lin_Bp, a->lin_b, nullptr, 0, y2, ws, ws_bytes, stream));
-  RUN(cdseg_add_layernorm(y2, nullptr, nullptr, nullptr, a->cpe_g, a->cpe_b, a->ln_eps, n, C, nullptr, y1, stream));
-  // residual (+ per-scene timestep projection) + norm1
   const float* tp = nullptr;
   if (a->t_scene) {
     RUN(cdseg_small_linear(a->t_scene, a->t_W, a->t_b, 0, a->B, a->T_dim, C, tproj, stream));
     tp = tproj;
   }
+  if (g_fused_mask & 4) {
+    // Linear (partials left unreduced) -> ONE kernel: reduce + bias + LayerNorm_cpe + residual (+ t) + norm1
+    int ns = 1;
+    RUN(run_linear_raw(y1, n, C, C, a->lin_Bp, a->lin_b, y2, ws, ws_bytes, stream, &ns));
+    RUN(cdseg_reduce_ln(ns > 1 ? (const float*)ws : y2, ns, ns > 1 ? a->lin_b : nullptr, a->cpe_g, a->cpe_b, a->x, tp, tp ? a->batch : nullptr,
+                        a->n1_g, a->n1_b, a->ln_eps, n, C, x1, h, stream));
+  } else {
+  RUN(run_linear(y1, n, C, C, a->lin_Bp, a->lin_b, nullptr, 0, y2, ws, ws_bytes, stream));
+  RUN(cdseg_add_layernorm(y2, nullptr, nullptr, nullptr, a->cpe_g, a->cpe_b, a->ln_eps, n, C, nullptr, y1, stream));
+  // residual (+ per-scene timestep projection) + norm1
   RUN(cdseg_add_layernorm(a->x, y1, tp, tp ? a->batch : nullptr, a->n1_g, a->n1_b, a->ln_eps, n, C, x1, h, stream));
+  }
   // attention
   RUN(run_linear(h, n, C, 3 * C, a->qkv_Bp, a->qkv_b, nullptr, 0, qkv, ws, ws_bytes, stream));
   }
@@ -117,9 +138,17 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
     if (a->ev[3]) cudaEventRecord((cudaEvent_t)a->ev[3], (cudaStream_t)stream);
     return CDSEG_OK;
   }
+  if (g_fused_mask & 4) {
+    // proj (partials left unreduced) -> ONE kernel: reduce + bias + residual + norm2
+    int ns = 1;
+    RUN(run_linear_raw(o, n, C, C, a->proj_Bp, a->proj_b, att, ws, ws_bytes, stream, &ns));
+    RUN(cdseg_reduce_ln(ns > 1 ? (const float*)ws : att, ns, ns > 1 ? a->proj_b : nullptr, nullptr, nullptr, x1, nullptr, nullptr, a->n2_g,
+                        a->n2_b, a->ln_eps, n, C, y2, h, stream));
+  } else {
   RUN(run_linear(o, n, C, C, a->proj_Bp, a->proj_b, nullptr, 0, att, ws, ws_bytes, stream));
   // residual + norm2 + MLP (fc1+GELU, fc2+residual fused in the GEMM epilogues)
   RUN(cdseg_add_layernorm(x1, att, nullptr, nullptr, a->n2_g, a->n2_b, a->ln_eps, n, C, y2, h, stream));
+  }
   if (a->ev[2]) cudaEventRecord((cudaEvent_t)a->ev[2], (cudaStream_t)stream);
   RUN(run_linear(h, n, C, 4 * C, a->fc1_Bp, a->fc1_b, nullptr, 1, hid, ws, ws_bytes, stream));
   if (a->ev[3]) cudaEventRecord((cudaEvent_t)a->ev[3], (cudaStream_t)stream);

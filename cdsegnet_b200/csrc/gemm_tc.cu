@@ -551,7 +551,7 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   if (dense3) gt::gemm_tc_kernel<3><<<g, gt::NTHREADS, smem, st>>>(p);
   else gt::gemm_tc_kernel<2><<<g, gt::NTHREADS, smem, st>>>(p);
   CDSEG_COUNT_LAUNCH(1);
-  if (nsplit > 1) {
+  if (nsplit > 1 && out) {                   // out == NULL: the caller consumes the raw partials part[z][M][N] itself (cdseg_reduce_ln)
     gt::splitk_reduce_kernel<<<cdseg_div_up(M * N, 256), 256, 0, st>>>((const float*)workspace, nsplit, M, N, bias, res,
                                                                        ldr, act, out, ldo);
     CDSEG_COUNT_LAUNCH(1);

@@ -75,6 +75,86 @@ CDSEG_API int cdseg_add_layernorm(const float* a, const float* b, const float* t
   return CDSEG_OK;
 }
 
+// Split-K reduction fused with the row-wise work that follows it in a Block of a deep level (C = 256 / 512, too wide for the
+// tensor-memory chained kernels): v = bias + sum_z part[z] -> [LayerNorm(g1, b1)] -> + res (+ t[batch]) -> y_out -> LayerNorm(g2, b2)
+// -> ln_out.  One launch instead of splitk_reduce + one or two add_layernorm launches (79 + 45 of the step's 571 launches were those).
+// Same summation order and LayerNorm formulas as the kernels it replaces, so results are bit-identical.  One warp per row.
+template <int VPL>
+__global__ void reduce_ln_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ bias, const float* __restrict__ g1,
+                                 const float* __restrict__ b1, const float* __restrict__ res, const float* __restrict__ t,
+                                 const int32_t* __restrict__ batch, const float* __restrict__ g2, const float* __restrict__ b2, float eps,
+                                 int64_t n, int C, float* __restrict__ y_out, float* __restrict__ ln_out) {
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float fc = (float)C;
+  float v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int c = lane + 32 * j;
+    float x = 0.f;
+    if (c < C) {
+      for (int z = 0; z < nsplit; ++z) x += part[((int64_t)z * n + row) * C + c];
+      if (bias) x += bias[c];
+    }
+    v[j] = x;
+    s += x;
+  }
+  if (g1) {
+    const float mean = warp_sum(s) / fc;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) { const float d = lane + 32 * j < C ? v[j] - mean : 0.f; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / fc + eps);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) { const int c = lane + 32 * j; if (c < C) v[j] = (v[j] - mean) * rstd * g1[c] + b1[c]; }
+  }
+  const float* tr = t ? t + (int64_t)batch[row] * C : nullptr;
+  s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int c = lane + 32 * j;
+    if (c < C) {
+      float x = v[j];
+      if (res) x = res[row * C + c] + x;
+      if (tr) x += tr[c];
+      if (y_out) y_out[row * C + c] = x;
+      v[j] = x;
+      s += x;
+    }
+  }
+  if (!ln_out) return;
+  const float mean = warp_sum(s) / fc;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) { const float d = lane + 32 * j < C ? v[j] - mean : 0.f; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / fc + eps);
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) { const int c = lane + 32 * j; if (c < C) ln_out[row * C + c] = (v[j] - mean) * rstd * g2[c] + b2[c]; }
+}
+
+// see include/cdseg_b200.h
+CDSEG_API int cdseg_reduce_ln(const float* part, int nsplit, const float* bias, const float* g1, const float* b1, const float* res,
+                              const float* t, const int32_t* batch, const float* g2, const float* b2, float eps, int64_t n, int C,
+                              float* y_out, float* ln_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!part || nsplit < 1 || C <= 0 || C > 1024 || (t && !batch) || (g1 && !b1) || (ln_out && (!g2 || !b2))) return CDSEG_EINVAL;
+  if (n == 0) return CDSEG_OK;
+  const int blocks = cdseg_div_up(n * 32, 256);
+#define LAUNCH_RL(V) reduce_ln_kernel<V><<<blocks, 256, 0, st>>>(part, nsplit, bias, g1, b1, res, t, batch, g2, b2, eps, n, C, y_out, ln_out)
+  if (C <= 32) LAUNCH_RL(1);
+  else if (C <= 64) LAUNCH_RL(2);
+  else if (C <= 128) LAUNCH_RL(4);
+  else if (C <= 256) LAUNCH_RL(8);
+  else if (C <= 512) LAUNCH_RL(16);
+  else LAUNCH_RL(32);
+#undef LAUNCH_RL
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
+
 // out = act(x * scale[c] + shift[c])   (scale/shift nullable; act: 0 none, 1 GELU(erf))
 __global__ void scale_shift_act_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
                                        const float* __restrict__ shift, int act, int64_t total4, int C4,

@@ -496,3 +496,14 @@ def criteria_grad(n_pred, n_target, ignore_index=-1, c_pred=None, c_target=None,
                                   float(weights[2]), int(has_mse), int(bool(has[1])), int(bool(has[2])), int(bool(gls)), _p(out), _p(gn),
                                   _p(gc), _p(ws), nb, _stream()), "criteria_grad")
     return out, gn, gc
+
+
+def reduce_ln(part, nsplit, bias=None, ln1=None, res=None, t=None, batch=None, ln2=None, eps=1e-5, want_y=True):
+    """v = bias + sum_z part[z] -> [LN(ln1)] -> + res (+ t[batch]) -> y -> LN(ln2): (y or None, ln or None).  part: [nsplit, n, C] fp32"""
+    _, n, C = part.shape
+    y = torch.empty((n, C), dtype=torch.float32, device=part.device) if want_y else None
+    o = torch.empty((n, C), dtype=torch.float32, device=part.device) if ln2 is not None else None
+    check(_lib.load().cdseg_reduce_ln(_p(part, torch.float32), nsplit, _p(bias), _p(ln1[0]) if ln1 else None, _p(ln1[1]) if ln1 else None,
+                                      _p(res), _p(t), _p(batch), _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None, float(eps), n, C,
+                                      _p(y), _p(o), _stream()), "reduce_ln")
+    return y, o

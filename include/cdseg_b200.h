@@ -118,6 +118,12 @@ int cdseg_attn_exact(const float* Q, const float* K, const float* V, const int32
 int cdseg_add_layernorm(const float* a, const float* b, const float* t, const int32_t* batch, const float* gamma,
                         const float* beta, float eps, int64_t n, int C, float* y_out, float* ln_out, void* stream);
 /* out = act(x*scale[c] + shift[c]); act 0 none, 1 GELU(erf) */
+/* split-K reduction fused with the row-wise tail of a Linear inside a Block: v = bias + sum_z part[z][n][C] (nsplit = 1: part is a
+ * finished [n, C] tensor) -> optional LayerNorm(g1, b1) -> + res (+ t[batch]) -> y_out (nullable) -> LayerNorm(g2, b2) -> ln_out (nullable).
+ * part = the workspace of a cdseg_gemm_tc call made with out = NULL and nsplit > 1 (partials left unreduced). */
+int cdseg_reduce_ln(const float* part, int nsplit, const float* bias, const float* g1, const float* b1, const float* res,
+                    const float* t, const int32_t* batch, const float* g2, const float* b2, float eps, int64_t n, int C,
+                    float* y_out, float* ln_out, void* stream);
 int cdseg_scale_shift_act(const float* x, const float* scale, const float* shift, int act, int64_t n, int C,
                           float* out, void* stream);
 /* out[r][o] = act(bias[o] + x[r].W[o]) for a handful of rows (per-scene timestep MLP); act 0 none, 2 swish */
@@ -179,7 +185,8 @@ int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, int C, const
 void cdseg_pre_attn_set_trace(long long* buf, int cta);
 size_t cdseg_conv_plan_bytes(int64_t n);
 int cdseg_conv_tile_plan(const int32_t* nbr, int64_t n, void* plan, void* stream);
-/* which fused kernels cdseg_block_forward uses: bit 0 post-attention chain, bit 1 pre-attention chain (default: all) */
+/* which fused kernels cdseg_block_forward uses: bit 0 post-attention chain, bit 1 pre-attention chain, bit 2 split-K reduction fused with
+ * the LayerNorms that follow it at the wide levels (default: all) */
 void cdseg_set_fused_mask(int mask);
 
 /* ---- native executor of one PTv3 Block (ptv3.py:399-428): the 12-13 launches above enqueued from C++ in one call --- */

@@ -467,3 +467,26 @@ def test_pre_attn_chain_vs_fp64(ops, counts, C, with_t, stale, curve):
     eq = (oq.cpu().double() - qkv).abs().max().item()
     assert e1 < 3e-5 * max(1.0, x1.abs().max().item()), e1
     assert eq < 5e-5 * max(1.0, qkv.abs().max().item()), eq
+
+
+@pytest.mark.parametrize("n,C,ns,with_ln1,with_t", [(990, 512, 8, True, True), (3800, 256, 4, False, False), (130, 96, 3, True, False), (7, 16, 1, True, True)])
+def test_reduce_ln_vs_fp64(ops, n, C, ns, with_ln1, with_t):
+    """split-K partial sums + bias -> [LayerNorm] -> + residual (+ per-scene t) -> LayerNorm in one launch == the fp64 composition"""
+    gen = torch.Generator().manual_seed(n + C)
+    part = torch.randn(ns, n, C, generator=gen)
+    bias, res = torch.randn(C, generator=gen), torch.randn(n, C, generator=gen)
+    g1, b1, g2, b2 = (torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen), torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen))
+    B = 3
+    t = torch.randn(B, C, generator=gen) if with_t else None
+    batch = torch.sort(torch.randint(0, B, (n,), generator=gen)).values.int()
+    d = lambda a: a.double()
+    v = d(part).sum(0) + d(bias)
+    if with_ln1:
+        v = torch.nn.functional.layer_norm(v, (C,), d(g1), d(b1), 1e-5)
+    y = d(res) + v + (d(t)[batch.long()] if with_t else 0)
+    ln = torch.nn.functional.layer_norm(y, (C,), d(g2), d(b2), 1e-5)
+    dev = lambda a: a.to(DEV) if a is not None else None
+    gy, gl = ops.reduce_ln(dev(part), ns, dev(bias), (dev(g1), dev(b1)) if with_ln1 else None, dev(res), dev(t), dev(batch) if with_t else None,
+                           (dev(g2), dev(b2)))
+    assert (gy.cpu().double() - y).abs().max() < 2e-5 * max(1.0, y.abs().max().item())
+    assert (gl.cpu().double() - ln).abs().max() < 5e-5 * max(1.0, ln.abs().max().item())
