@@ -95,7 +95,8 @@ __global__ void reduce_ln_kernel(const float* __restrict__ part, int nsplit, con
     const int c = lane + 32 * j;
     float x = 0.f;
     if (c < C) {
-      for (int z = 0; z < nsplit; ++z) x += part[((int64_t)z * n + row) * C + c];
+#pragma unroll 4
+      for (int z = 0; z < nsplit; ++z) x += __ldcg(part + ((int64_t)z * n + row) * C + c);     // loads hoisted, adds stay in z order
       if (bias) x += bias[c];
     }
     v[j] = x;
