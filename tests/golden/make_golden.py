@@ -286,6 +286,10 @@ def main():
     # BASELINE config 1: 2k-point room, CN only (condition=False), patch 128
     room = synth.collate([synth.small_room(2000, 0)])
     run_case(ptv3, comm, "case3_cn_only", room, cap=128, cfg_over=dict(condition=False))
+    # BASELINE config 4 shape: nuScenes-like sweeps, 4 input channels (coord + strength), 16 classes, grid 0.05 m => depth 11
+    if "case4" in sys.argv[1:] or len(sys.argv) == 1:
+        sweeps = synth.collate([synth.nuscenes_sweep(3000, 0), synth.nuscenes_sweep(2400, 1)])
+        run_case(ptv3, comm, "case4_nuscenes", sweeps, cap=64, cfg_over=dict(c_in_channels=4, n_in_channels=4, num_classes=16))
 
 
 if __name__ == "__main__":

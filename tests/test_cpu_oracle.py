@@ -72,7 +72,7 @@ def test_pool_plan_properties():
         assert (np.diff(pl["code"][r][pl["order"][r]]) > 0).all()
 
 
-@pytest.mark.parametrize("name", ["case1_single", "case2_batch2", "case3_cn_only"])
+@pytest.mark.parametrize("name", ["case1_single", "case2_batch2", "case3_cn_only", "case4_nuscenes"])
 def test_oracle_vs_reference_forward(name):
     """the functional fp32 oracle reproduces the reference network's outputs (dense branch)"""
     z, cfg, shapes = load_case(name)
