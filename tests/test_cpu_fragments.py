@@ -67,3 +67,29 @@ def test_knn_oracle_small_known_answers():
     assert np.allclose(d2, [[0.01, 0.81], [0.16, 0.36]], atol=1e-6)
     idx, d2 = K.knn_query(4, xyz, off, q, np.array([1, 2], dtype=np.int32))
     assert idx.tolist() == [[1, 0, 2, -1], [3, 4, -1, -1]] and d2[1, 2] == np.float32(1e10)
+
+
+def test_collect_fragment_host_logic_vs_reference():
+    """CenterShift(apply_z=False) + Collect(keys=(coord, grid_coord, index), feat_keys=(color, normal)) + collate_fn of one fragment
+    (transform.py:142-155, 26-50; datasets/utils.py:15-41) -- the host-side mirror in cdsegnet_b200.fragments on CPU tensors, fed with the
+    REFERENCE's own fragment 0 (its tie order), against the reference's model input"""
+    import torch
+    from cdsegnet_b200.fragments import collect_fragment, rotate_z
+    for i in range(4):
+        idx = Z[f"c{i}_index"][0]
+        part = dict(index=torch.from_numpy(idx), grid_coord=torch.from_numpy(Z[f"c{i}_grid"][idx]),
+                    coord=torch.from_numpy(Z[f"c{i}_coord"][idx]), color=torch.from_numpy(Z[f"c{i}_color"][idx]),
+                    normal=torch.from_numpy(Z[f"c{i}_normal"][idx]))
+        inp = collect_fragment(part)
+        assert np.array_equal(inp["coord"].numpy(), Z[f"c{i}_in_coord"])           # float32 arithmetic like numpy's: bit-exact
+        assert np.array_equal(inp["feat"].numpy(), Z[f"c{i}_in_feat"])
+        assert np.array_equal(inp["grid_coord"].numpy(), Z[f"c{i}_in_grid_coord"])
+        assert np.array_equal(inp["index"].numpy(), Z[f"c{i}_in_index"])
+        assert np.array_equal(inp["offset"].numpy(), Z[f"c{i}_in_offset"])
+    # the TTA rotation: float64 result like np.dot(float32, float64) in RandomRotateTargetAngle (transform.py:259-294)
+    c = torch.from_numpy(Z["c0_coord"])
+    out = rotate_z(0.5)(dict(coord=c, normal=torch.from_numpy(Z["c0_normal"])))
+    a = 0.5 * np.pi
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    assert out["coord"].dtype == torch.float64 and np.allclose(out["coord"].numpy(), np.dot(Z["c0_coord"], R.T), rtol=0, atol=1e-12)
+    assert np.allclose(out["normal"].numpy(), np.dot(Z["c0_normal"], R.T), atol=1e-12)
