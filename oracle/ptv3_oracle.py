@@ -115,8 +115,15 @@ def segment_mean(src, cluster, counts):
     return out / counts[:, None].to(src.dtype)
 
 
+BN_TRAIN = False      # True: BatchNorm normalises with the statistics of the batch (nn.BatchNorm1d in train mode) -- the training oracle
+
+
 def bn_eval(x, sd, p, eps=1e-3):
-    """nn.BatchNorm1d(eps=1e-3, momentum=0.01) in eval mode (ptv3.py:1435)."""
+    """nn.BatchNorm1d(eps=1e-3, momentum=0.01) (ptv3.py:1435): running statistics in eval mode, batch statistics (biased variance) when
+    BN_TRAIN is set (the running-statistics update is not restated: it does not enter the loss or the gradients)."""
+    if BN_TRAIN:
+        mean, var = x.mean(0), x.var(0, unbiased=False)
+        return (x - mean) / torch.sqrt(var + eps) * sd[p + "weight"] + sd[p + "bias"]
     return (x - sd[p + "running_mean"]) / torch.sqrt(sd[p + "running_var"] + eps) * sd[p + "weight"] + sd[p + "bias"]
 
 
@@ -367,8 +374,12 @@ def _dstage(sd, prefix, s, point, depth, heads, patch, n_orders, has_t, mode, sk
     return point
 
 
-@torch.no_grad()
 def forward(sd, cfg, c_in=None, n_in=None, attn_mode="dense", perm_fn=None, trace=None):
+    with torch.set_grad_enabled(any(torch.is_tensor(v) and v.requires_grad for v in sd.values())):     # autograd only for the training oracle
+        return _forward(sd, cfg, c_in, n_in, attn_mode, perm_fn, trace)
+
+
+def _forward(sd, cfg, c_in=None, n_in=None, attn_mode="dense", perm_fn=None, trace=None):
     """PointTransformerV3.forward (ptv3.py:1757-1845), eval mode.
 
     sd: state_dict of the *backbone* (keys like ``_n_enc.enc0.block0...``).

@@ -136,3 +136,22 @@ def criteria(point, loss_type="EW", task_num=2, ignore_index=-1, weights=(1.0, 1
     else:
         loss = parts[0] * (parts[1] + parts[2])
     return torch.pow(torch.as_tensor(loss), 1.0 / task_num), parts
+
+
+# ---------------------------------------------------------------------------------------------- training pass
+def training_loss(bsd, cfg, input_dict, ts, noise, abar32, loss_type="GLS", task_num=2, ignore_index=-1, dm_target="noise",
+                  perm_fn=None, attn_mode="dense"):
+    """DefaultSegmentorV2.forward (default.py:424-493) for condition=True, dm=True with the two random draws injected: ts int64 [B,1]
+    (timestep per scene) and noise fp32 [N, C_in].  bsd = backbone state_dict (tensors may require grad: autograd then yields the
+    reference's parameter gradients); BatchNorm follows ptv3_oracle.BN_TRAIN.  Returns (loss, [mse, ce, lovasz])."""
+    from . import ptv3_oracle as O
+    base = dict(coord=input_dict["coord"], grid_coord=input_dict["grid_coord"], offset=input_dict["offset"])
+    counts = torch.diff(input_dict["offset"], prepend=input_dict["offset"].new_zeros(1))
+    batch = torch.repeat_interleave(torch.arange(len(counts)), counts)
+    x0 = input_dict["feat"]
+    t_emb = O.calc_t_emb(ts, cfg["T_dim"])[batch]
+    x_t = q_sample(abar32, x0, ts[batch], noise)
+    c_out, n_out = O.forward(bsd, cfg, dict(base, feat=x_t, t_emb=t_emb), dict(base, feat=x0), attn_mode=attn_mode, perm_fn=perm_fn)
+    point = dict(c_pred=c_out["feat"], c_target=noise if dm_target == "noise" else x0, n_pred=n_out["feat"], n_target=input_dict["segment"],
+                 loss_mode="train")
+    return criteria(point, loss_type, task_num, ignore_index)
