@@ -13,6 +13,15 @@ Pinning status (see DESIGN.md "Oracle"):
     PTv3 dual-network wiring: PINNED against outputs of the reference's own
     python sources executed in the authoring container
     (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz|*.pt``).
+  * the DefaultSegmentorV2 wrapper (diffusion schedule, q / DDIM samplers, criteria, inference / inference_ddim / forward) --
+    ``wrapper_oracle.py``: PINNED by ``tests/golden/make_golden_wrapper.py`` (reference default.py + losses/*.py executed);
+  * the training pass (train-mode forward + autograd gradients) -- ``wrapper_oracle.training_loss`` + ``ptv3_oracle.BN_TRAIN``:
+    PINNED by ``tests/golden/make_golden_train.py`` (reference forward + loss.backward() executed);
+  * test-time GridSample / FNV + ravel hashes / collate / voting -- ``fragments_np.py``: PINNED by
+    ``tests/golden/make_golden_fragments.py`` (reference transform.py + datasets/utils.py executed), except the tie order inside a
+    voxel, which the reference's unstable ``np.argsort`` leaves unspecified;
+  * ``pointops.knn_query`` -- ``knn_np.py``: PINNED on the GPU box against the reference's OWN CUDA kernel, compiled by
+    ``oracle/Makefile`` into ``oracle/_ref/libref_knn.so`` from the sources where they lie under /root/reference;
   * spconv ``SubMConv3d`` tap order / weight layout, ``torch_scatter.segment_csr``
     and ``flash_attn`` numerics: third-party packages that are NOT vendored in the
     reference tree -> "parity unpinned" for those three (semantics restated from
