@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
-SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "losses.cu", "fragments.cu", "knn.cu"]
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "attn_tc3.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "losses.cu", "fragments.cu", "knn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
@@ -72,7 +72,7 @@ class BlockArgs(ctypes.Structure):
                 ("conv_Bp", _P), ("conv_b", _P), ("lin_Bp", _P), ("lin_b", _P), ("cpe_g", _P), ("cpe_b", _P),
                 ("t_W", _P), ("t_b", _P), ("n1_g", _P), ("n1_b", _P), ("qkv_Bp", _P), ("qkv_b", _P), ("proj_Bp", _P),
                 ("proj_b", _P), ("n2_g", _P), ("n2_b", _P), ("fc1_Bp", _P), ("fc1_b", _P), ("fc2_Bp", _P), ("fc2_b", _P),
-                ("ln_eps", _F), ("out", _P), ("scratch", _P), ("scratch_bytes", _Z), ("ev", _P * 6)]
+                ("ln_eps", _F), ("attn_mode", _I), ("out", _P), ("scratch", _P), ("scratch_bytes", _Z), ("ev", _P * 6)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/cdseg_b200.h
@@ -105,6 +105,8 @@ SIGNATURES = {
     "cdseg_attn_tc2": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
     "cdseg_attn_tc_smem_bytes": (_Z, [_I]),
     "cdseg_attn_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
+    "cdseg_attn_pack_split": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "cdseg_attn_tc3": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P, _L, _P]),
     "cdseg_attn_exact": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
     "cdseg_add_layernorm": (_I, [_P, _P, _P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),
     "cdseg_reduce_ln": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),

@@ -95,6 +95,68 @@ CDSEG_API int cdseg_attn_pack_f16v(const float* src, int64_t ld, int col0, int C
   return CDSEG_OK;
 }
 
+// hi/lo split packing for cdseg_attn_tc3 mode 1 (fp32-class attention on the tensor cores): x = hi + lo with hi = fp16(x),
+// lo = fp16(x - hi).  q / k tensors: the hi halves of all (head, patch) blocks in the [H][T][Kp][16] core-matrix layout, followed
+// by the lo halves in the same layout (2 * H*T*Kp*16 halves per tensor).  The V tensor (index v_which, -1: none) is written 48 wide
+// per key, [v_hi(16) | 1 | 0 x 15 | v_lo(16)], block layout (k/8)*384 + (n/8)*64 + (k%8)*8 + n%8 (MN-major B operand).
+__global__ void pack_split_kernel(const float* __restrict__ src, int64_t ld, int col0, int C, int nwhich,
+                                  const int32_t* __restrict__ slot_src, int H, int T, int Kp, __half* __restrict__ dst0,
+                                  __half* __restrict__ dst1, __half* __restrict__ dst2, int v_which) {
+  const int64_t slots = (int64_t)T * Kp;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (tid >= slots * H * nwhich) return;
+  const int64_t p = tid % slots;
+  const int h = (int)((tid / slots) % H);
+  const int which = (int)(tid / (slots * H));
+  const int t = (int)(p / Kp), r = (int)(p % Kp);
+  const int32_t s = slot_src[p];
+  float v[16];
+  if (s >= 0) {
+    const float4* row = reinterpret_cast<const float4*>(src + (int64_t)s * ld + col0 + which * C + h * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float4 q = row[j]; v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  }
+  __half2 hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    const float2 b = __half22float2(hi[j]);
+    lo[j] = __floats2half2_rn(v[2 * j] - b.x, v[2 * j + 1] - b.y);
+  }
+  __half* dst = which == 0 ? dst0 : (which == 1 ? dst1 : dst2);
+  if (which == v_which) {
+    uint4* o = reinterpret_cast<uint4*>(dst + ((int64_t)h * T + t) * Kp * 48 + (r / 8) * 384 + (r % 8) * 8);
+    o[0] = *reinterpret_cast<uint4*>(&hi[0]);
+    o[8] = *reinterpret_cast<uint4*>(&hi[4]);
+    o[16] = make_uint4(s >= 0 ? 0x00003C00u : 0u, 0u, 0u, 0u);                 // n 16 = 1.0 (valid keys)
+    o[24] = make_uint4(0u, 0u, 0u, 0u);
+    o[32] = *reinterpret_cast<uint4*>(&lo[0]);
+    o[40] = *reinterpret_cast<uint4*>(&lo[4]);
+    return;
+  }
+  __half* blk = dst + ((int64_t)h * T + t) * Kp * 16 + (r / 8) * 128 + (r % 8) * 8;
+  uint4* oh = reinterpret_cast<uint4*>(blk);
+  uint4* ol = reinterpret_cast<uint4*>(blk + (int64_t)H * T * Kp * 16);
+  oh[0] = *reinterpret_cast<uint4*>(&hi[0]); oh[8] = *reinterpret_cast<uint4*>(&hi[4]);
+  ol[0] = *reinterpret_cast<uint4*>(&lo[0]); ol[8] = *reinterpret_cast<uint4*>(&lo[4]);
+}
+
+// has_v != 0: the LAST of the nwhich tensors is V (48 wide); the others are q / k (hi | lo).
+CDSEG_API int cdseg_attn_pack_split(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src, int H, int T,
+                                    int Kp, void* dst0, void* dst1, void* dst2, int has_v, void* stream) {
+  if (H <= 0 || C != H * 16 || nwhich < 1 || nwhich > 3 || (Kp % 128) || (ld & 3) || (col0 & 3)) return CDSEG_EINVAL;
+  const int64_t total = (int64_t)T * Kp * H * nwhich;
+  if (total == 0) return CDSEG_OK;
+  pack_split_kernel<<<cdseg_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, col0, C, nwhich, slot_src, H, T, Kp, (__half*)dst0,
+                                                                               (__half*)dst1, (__half*)dst2, has_v ? nwhich - 1 : -1);
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
+
 CDSEG_API int cdseg_attn_pack_f32(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src,
                                   int H, int T, int Kp, float* dst0, float* dst1, float* dst2, void* stream) {
   if (H <= 0 || C != H * 16 || nwhich < 1 || nwhich > 3 || (Kp % 128) || (ld & 3) || (col0 & 3)) return CDSEG_EINVAL;

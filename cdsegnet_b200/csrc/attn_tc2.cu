@@ -305,8 +305,8 @@ attn_tc2_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
 // Q, K: fp16 packed [H][T][Kp][16]; V: fp16 packed 32 wide [H][T][Kp][32] with the ones column (cdseg_attn_pack_f16v, v_ones=1).
 // out: fp32 [n, out_ld]; head h -> columns h*16 .. h*16+15 of row slot_dst[slot].
 // exponentials per group of 8 computed on the FMA pipe instead of MUFU (0..3); env CDSEG_ATTN_POLY or cdseg_attn_set_poly
-static int g_attn_poly = [] { const char* e = getenv("CDSEG_ATTN_POLY"); return e ? atoi(e) : 0; }();
-CDSEG_API void cdseg_attn_set_poly(int per8) { g_attn_poly = per8 < 0 ? 0 : (per8 > 3 ? 3 : per8); }
+extern int g_cdseg_attn_poly;      // attn_tc3.cu (cdseg_attn_set_poly)
+#define g_attn_poly g_cdseg_attn_poly
 
 CDSEG_API int cdseg_attn_tc2(const void* Q, const void* K, const void* V32, const int32_t* patch_len,
                              const int32_t* slot_dst, int H, int T, int Kp, float scale, float* out, int64_t out_ld,

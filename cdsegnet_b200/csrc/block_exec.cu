@@ -52,7 +52,8 @@ CDSEG_API size_t cdseg_block_scratch_bytes(int64_t n, int C, int H, int T, int K
   s += 6 * row;                                   // y1, y2, x1, h, o, a  (a doubles as x2-input)
   s += align_up((size_t)n * 3 * C * 4);           // qkv
   s += align_up((size_t)n * 4 * C * 4);           // hidden
-  s += 4 * align_up((size_t)H * T * Kp * 16 * 2); // packed q, k (16 wide) and v (32 wide: [v | 1 | 0..]) in fp16
+  s += 7 * align_up((size_t)H * T * Kp * 16 * 2); // packed q, k (16 wide) and v (32 wide: [v | 1 | 0..]) in fp16; CDSEG_ATTN_EXACT packs fp32 q, k, v
+                                                  // (3 x 2 units); CDSEG_ATTN_TC32 packs q / k as fp16 hi | lo (2 + 2) and v 48 wide (3): 7 units
   s += align_up((size_t)B * C * 4);               // t projection
   s += (size_t)32 << 20;                          // split-K partials: only launches with < 120 output tiles split, so
                                                   // nsplit * M * N * 4 B stays below ~26 MB (see pick_split)
@@ -75,7 +76,10 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
   float* qkv = (float*)take((size_t)n * 3 * C * 4);
   float* hid = (float*)take((size_t)n * 4 * C * 4);
   const size_t pk = (size_t)a->H * a->T * a->Kp * 16 * 2;
-  void* qp = take(pk); void* kp = take(pk); void* vp = take(2 * pk);
+  const int am = a->attn_mode;
+  if (am != CDSEG_ATTN_F16 && am != CDSEG_ATTN_EXACT && am != CDSEG_ATTN_TC32) return CDSEG_EINVAL;
+  const size_t qk_units = am == CDSEG_ATTN_F16 ? 1 : 2, v_units = am == CDSEG_ATTN_TC32 ? 3 : 2;
+  void* qp = take(qk_units * pk); void* kp = take(qk_units * pk); void* vp = take(v_units * pk);
   float* tproj = (float*)take((size_t)a->B * C * 4);
   if (p > end) return CDSEG_ENOSPC;
   void* ws = p;
@@ -126,9 +130,20 @@ CDSEG_API int cdseg_block_forward(const CdsegBlockArgs* a, void* stream) {
   // attention
   RUN(run_linear(h, n, C, 3 * C, a->qkv_Bp, a->qkv_b, nullptr, 0, qkv, ws, ws_bytes, stream));
   }
-  RUN(cdseg_attn_pack_f16v(qkv, 3 * C, 0, C, 3, a->slot_src, a->H, a->T, a->Kp, qp, kp, vp, 1, stream));
-  if (a->ev[0]) cudaEventRecord((cudaEvent_t)a->ev[0], (cudaStream_t)stream);
-  RUN(cdseg_attn_tc2(qp, kp, vp, a->patch_len, a->slot_dst, a->H, a->T, a->Kp, a->scale, o, C, stream));
+  if (am == CDSEG_ATTN_EXACT) {       // dense-branch numerics (ptv3.py:264-280): fp32 operands, SIMT kernel
+    RUN(cdseg_attn_pack_f32(qkv, 3 * C, 0, C, 3, a->slot_src, a->H, a->T, a->Kp, (float*)qp, (float*)kp, (float*)vp, stream));
+    if (a->ev[0]) cudaEventRecord((cudaEvent_t)a->ev[0], (cudaStream_t)stream);
+    RUN(cdseg_attn_exact((const float*)qp, (const float*)kp, (const float*)vp, a->patch_len, a->slot_dst, a->H, a->T, a->Kp, a->scale, o, C,
+                         stream));
+  } else if (am == CDSEG_ATTN_TC32) { // tcgen05 with hi/lo-split operands: fp32-class results at tensor-core speed
+    RUN(cdseg_attn_pack_split(qkv, 3 * C, 0, C, 3, a->slot_src, a->H, a->T, a->Kp, qp, kp, vp, 1, stream));
+    if (a->ev[0]) cudaEventRecord((cudaEvent_t)a->ev[0], (cudaStream_t)stream);
+    RUN(cdseg_attn_tc3(qp, kp, vp, a->patch_len, a->slot_dst, a->H, a->T, a->Kp, a->scale, 1, o, C, stream));
+  } else {                            // flash-branch numerics (ptv3.py:282-289): fp16 operands / probabilities / output
+    RUN(cdseg_attn_pack_f16v(qkv, 3 * C, 0, C, 3, a->slot_src, a->H, a->T, a->Kp, qp, kp, vp, 1, stream));
+    if (a->ev[0]) cudaEventRecord((cudaEvent_t)a->ev[0], (cudaStream_t)stream);
+    RUN(cdseg_attn_tc3(qp, kp, vp, a->patch_len, a->slot_dst, a->H, a->T, a->Kp, a->scale, 0, o, C, stream));
+  }
   if (a->ev[1]) cudaEventRecord((cudaEvent_t)a->ev[1], (cudaStream_t)stream);
   if ((g_fused_mask & 1) && fused_c) {
     // proj + residual + norm2 + MLP + residual: one kernel, intermediates in tensor memory (fused_post.cu)

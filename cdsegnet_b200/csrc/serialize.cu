@@ -16,7 +16,7 @@ unsigned long long g_cdseg_launches = 0;
 
 CDSEG_API unsigned long long cdseg_launch_count(void) { return g_cdseg_launches; }
 CDSEG_API void cdseg_launch_count_reset(void) { g_cdseg_launches = 0; }
-CDSEG_API int cdseg_abi_version(void) { return 1; }
+CDSEG_API int cdseg_abi_version(void) { return 2; }
 
 // ---------------------------------------------------------------------------------
 // grid max (for serialized_depth = bit_length(max), structure.py:66)

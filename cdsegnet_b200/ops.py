@@ -222,35 +222,57 @@ def conv_im2col_tc(x8, nbr, Bp, N, bias, act):
 
 
 # ---------------------------------------------------------------- attention
-ATTN_V2 = True        # tcgen05 attention generation: True = attn_tc2.cu (streamed K/V, merged [V|1] operand), False = attn_tc.cu
+ATTN_KERNEL = 3       # tcgen05 attention generation behind mode "f16": 3 = attn_tc3.cu (deferred fold, double-buffered P / O),
+                      # 2 = attn_tc2.cu (round 1), 1 = attn_tc.cu (whole-patch K/V image); 2 and 1 are kept as A/B comparators
+ATTN_MODES = ("f16", "exact", "tc32")      # index = CDSEG_ATTN_F16 / _EXACT / _TC32 (include/cdseg_b200.h)
 
 
-def attn_pack(src, col0, C, nwhich, pm, H, exact=False, has_v=True):
-    """Gather rows of src (fp32 [n, ld]) by pm['slot_src'] into per-(head, patch) tiles.  With the v2 tensor-core
-    kernel the last tensor (V, when has_v) is packed 32 wide with the ones column."""
+def attn_pack(src, col0, C, nwhich, pm, H, mode="f16", has_v=True):
+    """Gather rows of src (fp32 [n, ld]) by pm['slot_src'] into per-(head, patch) operand tiles of the attention kernel of `mode`:
+      "f16"   fp16 core-matrix tiles, V 32 wide with the ones column (flash-branch numerics, ptv3.py:282-289)
+      "tc32"  fp16 hi | lo halves of q / k, V 48 wide [v_hi | 1 | v_lo] (fp32-class results on the tensor cores)
+      "exact" plain fp32 rows (SIMT dense-branch kernel, ptv3.py:264-280)"""
     lib = _lib.load()
     T, Kp = pm["T"], pm["Kp"]
-    dt = torch.float32 if exact else torch.float16
-    v32 = (not exact) and ATTN_V2 and has_v
-    bufs = [torch.empty((H, T, Kp, 32 if (v32 and i == nwhich - 1) else 16), dtype=dt, device=src.device) for i in range(nwhich)]
-    ptrs = [_p(b) for b in bufs] + [None] * (3 - nwhich)
-    if exact:
+    dev = src.device
+    if mode == "exact":
+        bufs = [torch.empty((H, T, Kp, 16), dtype=torch.float32, device=dev) for _ in range(nwhich)]
+        ptrs = [_p(b) for b in bufs] + [None] * (3 - nwhich)
         check(lib.cdseg_attn_pack_f32(_p(src, torch.float32), src.shape[1], col0, C, nwhich, _p(pm["slot_src"]), H, T, Kp, *ptrs,
                                       _stream()), "attn_pack")
-    else:
-        check(lib.cdseg_attn_pack_f16v(_p(src, torch.float32), src.shape[1], col0, C, nwhich, _p(pm["slot_src"]), H, T, Kp, *ptrs,
-                                       int(v32), _stream()), "attn_pack")
+        return bufs
+    if mode == "tc32":
+        bufs = [torch.empty((H, T, Kp, 48) if (has_v and i == nwhich - 1) else (2, H, T, Kp, 16), dtype=torch.float16, device=dev)
+                for i in range(nwhich)]
+        ptrs = [_p(b) for b in bufs] + [None] * (3 - nwhich)
+        check(lib.cdseg_attn_pack_split(_p(src, torch.float32), src.shape[1], col0, C, nwhich, _p(pm["slot_src"]), H, T, Kp, *ptrs,
+                                        int(has_v), _stream()), "attn_pack_split")
+        return bufs
+    if mode != "f16":
+        raise ValueError(f"attention mode {mode!r} not in {ATTN_MODES}")
+    v32 = ATTN_KERNEL >= 2 and has_v
+    bufs = [torch.empty((H, T, Kp, 32 if (v32 and i == nwhich - 1) else 16), dtype=torch.float16, device=dev) for i in range(nwhich)]
+    ptrs = [_p(b) for b in bufs] + [None] * (3 - nwhich)
+    check(lib.cdseg_attn_pack_f16v(_p(src, torch.float32), src.shape[1], col0, C, nwhich, _p(pm["slot_src"]), H, T, Kp, *ptrs,
+                                   int(v32), _stream()), "attn_pack")
     return bufs
 
 
-def attn(q, k, v, pm, H, scale, n_out, exact=False):
+def attn(q, k, v, pm, H, scale, n_out, mode="f16"):
     """softmax(q k^T * scale) v per (patch, head); rows scattered to original point order."""
     lib = _lib.load()
     C = H * 16
     out = torch.empty((n_out, C), dtype=torch.float32, device=q.device)
-    fn = lib.cdseg_attn_exact if exact else (lib.cdseg_attn_tc2 if v.shape[-1] == 32 else lib.cdseg_attn_tc)
-    check(fn(_p(q), _p(k), _p(v), _p(pm["patch_len"]), _p(pm["slot_dst"]), H, pm["T"], pm["Kp"], float(scale), _p(out),
-             C, _stream()), "attn")
+    args = (_p(q), _p(k), _p(v), _p(pm["patch_len"]), _p(pm["slot_dst"]), H, pm["T"], pm["Kp"], float(scale))
+    if mode == "exact":
+        st = lib.cdseg_attn_exact(*args, _p(out), C, _stream())
+    elif mode == "tc32":
+        st = lib.cdseg_attn_tc3(*args, 1, _p(out), C, _stream())
+    elif ATTN_KERNEL == 3:
+        st = lib.cdseg_attn_tc3(*args, 0, _p(out), C, _stream())
+    else:
+        st = (lib.cdseg_attn_tc2 if v.shape[-1] == 32 else lib.cdseg_attn_tc)(*args, _p(out), C, _stream())
+    check(st, "attn")
     return out
 
 

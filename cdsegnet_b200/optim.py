@@ -30,7 +30,8 @@ class FusedAdamW(torch.optim.Optimizer):
     def _table(self, gi, group):
         """device table of this group's chunks; rebuilt when a gradient buffer moved (torch may re-allocate .grad)"""
         ps = [p for p in group["params"] if p.grad is not None]
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr() if self.state[p] else 0,
+                     self.state[p]["exp_avg_sq"].data_ptr() if self.state[p] else 0) for p in ps)   # load_state_dict replaces the moments
         hit = self._tables.get(gi)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
@@ -72,6 +73,9 @@ class FusedAdamW(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             check(lib.cdseg_adamw_step(table.data_ptr(), n, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                        float(group["weight_decay"]), int(step), _stream()), "adamw_step")
+            # the kernel writes through raw pointers: tell torch the parameters changed, so that everything keyed on
+            # Parameter._version (the packed tensor-core operand caches of ptv3.py) is rebuilt before the next forward
+            torch._C._increment_version(ps)
         return loss
 
 

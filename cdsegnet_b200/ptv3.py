@@ -139,9 +139,10 @@ _PACK = _PackCache()
 def packed_linear(w, b=None):
     """(packed tensor-core operand blocks, fp32 bias) of a plain Linear, cached (shared with linear())"""
     def build():
-        bf = b.detach().float().contiguous() if b is not None else None
+        # qkv_bias=False: the fused kernels always add a bias vector, so a missing one becomes zeros
+        bf = b.detach().float().contiguous() if b is not None else torch.zeros(w.shape[0], dtype=torch.float32, device=w.device)
         return ops.gemm_pack_b(w.detach().float().t().contiguous()[None]), bf
-    return _PACK.get((id(w), None), [w, b], build)
+    return _PACK.get((id(w), "packed"), [w, b], build)
 
 
 def linear(x, w, b=None, act=0, res=None, bn=None, cols=None):
@@ -205,7 +206,7 @@ class MLP(nn.Module):
 
 
 class SerializedAttention(nn.Module):
-    """ptv3.py:125-296 (flash-branch semantics; ``exact`` selects fp32 dense-branch numerics)."""
+    """ptv3.py:125-296.  ``mode`` (ops.ATTN_MODES): "f16" = flash-branch numerics, "tc32" / "exact" = dense-branch (fp32) numerics."""
 
     def __init__(self, channels, num_heads, patch_size, qkv_bias=True, qk_scale=None, order_index=0):
         super().__init__()
@@ -219,11 +220,11 @@ class SerializedAttention(nn.Module):
         self.qkv = nn.Linear(channels, channels * 3, bias=qkv_bias)
         self.proj = nn.Linear(channels, channels)
 
-    def forward(self, x, level, exact):
+    def forward(self, x, level, mode):
         pm = level.patch_maps(self.order_index, self.patch_size)
         qkv = linear(x, self.qkv.weight, self.qkv.bias)
-        q, k, v = ops.attn_pack(qkv, 0, self.channels, 3, pm, self.num_heads, exact)
-        o = ops.attn(q, k, v, pm, self.num_heads, self.scale, x.shape[0], exact)
+        q, k, v = ops.attn_pack(qkv, 0, self.channels, 3, pm, self.num_heads, mode)
+        o = ops.attn(q, k, v, pm, self.num_heads, self.scale, x.shape[0], mode)
         return linear(o, self.proj.weight, self.proj.bias)
 
 
@@ -242,7 +243,7 @@ class Block(nn.Module):
         if T_dim != -1:
             self.t_mlp = nn.Linear(T_dim, channels)
 
-    def _native(self, point, level):
+    def _native(self, point, level, mode):
         """the whole block through ONE C-ABI call (cdseg_block_forward): same kernels, enqueued from C++"""
         import ctypes
         from ._lib import BlockArgs, load, check
@@ -272,6 +273,7 @@ class Block(nn.Module):
         a.n1_g, a.n1_b = self.norm1[0].weight.data_ptr(), self.norm1[0].bias.data_ptr()
         a.n2_g, a.n2_b = self.norm2[0].weight.data_ptr(), self.norm2[0].bias.data_ptr()
         a.ln_eps = self.norm1[0].eps
+        a.attn_mode = ops.ATTN_MODES.index(mode)           # CDSEG_ATTN_F16 / _TC32 / _EXACT
         lib = load()
         need = lib.cdseg_block_scratch_bytes(n, C, a.H, a.T, a.Kp, a.B)
         arena = ops.arena(need, x.device)
@@ -286,11 +288,11 @@ class Block(nn.Module):
         point["feat"] = out
         return point
 
-    def forward(self, point, exact):
+    def forward(self, point, mode):
         level = point["_level"]
-        if (ops.GEMM_MODE == "tc" and ops.NATIVE_BLOCKS and not exact
+        if (ops.GEMM_MODE == "tc" and ops.NATIVE_BLOCKS and (mode != "f16" or ops.ATTN_KERNEL == 3)
                 and (self.T_dim == -1 or "t_scene" in point or "t_emb" not in point)):
-            return self._native(point, level)
+            return self._native(point, level, mode)
         x = point["feat"]
         conv_in = point.pop("conv_in", x)             # stale sparse_conv_feat quirk, see SerializedUnpooling
         y = self.cpe[0](conv_in, level)
@@ -304,7 +306,7 @@ class Block(nn.Module):
             y = linear(point["t_emb"], self.t_mlp.weight, self.t_mlp.bias, res=y)
         n1 = self.norm1[0]
         x1, h = ops.add_layernorm(x, y, t, tb, n1.weight, n1.bias, n1.eps)
-        a = self.attn(h, level, exact)
+        a = self.attn(h, level, mode)
         n2 = self.norm2[0]
         x2, h = ops.add_layernorm(x1, a, gamma=n2.weight, beta=n2.bias, eps=n2.eps)
         point["feat"] = self.mlp[0](h, res=x2)
@@ -419,15 +421,15 @@ class SerializedCrossAttention(nn.Module):
         self.kv = nn.Linear(kv_channels, q_channels * 2, bias=qkv_bias)
         self.proj = nn.Linear(q_channels, q_channels)
 
-    def forward(self, xq, q_level, xkv, kv_level, exact):
+    def forward(self, xq, q_level, xkv, kv_level, mode):
         pm = q_level.patch_maps(self.order_index, self.K)
         if q_level.n != kv_level.n:
             raise ValueError("TransferModule needs equally sized q / kv levels (ptv3.py:1008-1010)")
         kv_row = kv_level.order[kv_level.rowmap[self.order_index]][: kv_level.n]
         pm_kv = ops.patch_maps(kv_row, q_level.scene_count(), pm["K"])
-        (q,) = ops.attn_pack(linear(xq, self.q.weight, self.q.bias), 0, self.C, 1, pm, self.H, exact, has_v=False)
-        k, v = ops.attn_pack(linear(xkv, self.kv.weight, self.kv.bias), 0, self.C, 2, pm_kv, self.H, exact)
-        o = ops.attn(q, k, v, pm, self.H, self.scale, xq.shape[0], exact)
+        (q,) = ops.attn_pack(linear(xq, self.q.weight, self.q.bias), 0, self.C, 1, pm, self.H, mode, has_v=False)
+        k, v = ops.attn_pack(linear(xkv, self.kv.weight, self.kv.bias), 0, self.C, 2, pm_kv, self.H, mode)
+        o = ops.attn(q, k, v, pm, self.H, self.scale, xq.shape[0], mode)
         return linear(o, self.proj.weight, self.proj.bias)
 
 
@@ -455,7 +457,7 @@ class CrossBlock(nn.Module):
         y = linear(seq[0](x, level), seq[1].weight, seq[1].bias)
         return ops.add_layernorm(y, gamma=seq[2].weight, beta=seq[2].bias, eps=seq[2].eps, want_sum=False)[1]
 
-    def forward(self, q_point, kv_point, exact):
+    def forward(self, q_point, kv_point, mode):
         ql, kl = q_point["_level"], kv_point["_level"]
         xq, xkv = q_point["feat"], kv_point["feat"]
         n1, k1, n2 = self.q_norm1[0], self.kv_norm1[0], self.q_norm2[0]
@@ -463,7 +465,7 @@ class CrossBlock(nn.Module):
         _, hkv = ops.add_layernorm(xkv, self._cpe(self.kv_cpe, xkv, kl), gamma=k1.weight, beta=k1.bias, eps=k1.eps,
                                    want_sum=False)
         kv_point["feat"] = hkv                      # the reference leaves LN(kv) in kv_point.feat (ptv3.py:1190-1192)
-        a = self.attn(hq, ql, hkv, kl, exact)
+        a = self.attn(hq, ql, hkv, kl, mode)
         if self.tm_feat != 1.0:
             a = a * self.tm_feat
         q2, h = ops.add_layernorm(q1, a, gamma=n2.weight, beta=n2.bias, eps=n2.eps)
@@ -478,8 +480,8 @@ class TransferModule(nn.Module):
             raise NotImplementedError("tm_bidirectional=True is not used by any shipped config")
         self.cross_block2 = CrossBlock(**kw)
 
-    def forward(self, c_point, n_point, exact):
-        return c_point, self.cross_block2(n_point, c_point, exact)
+    def forward(self, c_point, n_point, mode):
+        return c_point, self.cross_block2(n_point, c_point, mode)
 
 
 class PointTransformerV3(nn.Module):
@@ -509,13 +511,16 @@ class PointTransformerV3(nn.Module):
         self.condition = condition
         self.T_dim = T_dim
         self.num_classes = num_classes
-        # enable_flash=True -> fp16 tensor-core attention (the reference's flash branch);
-        # enable_flash=False -> exact fp32 attention (the reference's dense branch)
-        self.exact_attention = not enable_flash
+        # attention numerics (ops.ATTN_MODES).  enable_flash=True -> "f16": fp16 operands / probabilities / output on the tensor
+        # cores = the reference's flash branch (ptv3.py:282-289).  enable_flash=False -> "tc32": the reference's dense fp32 branch
+        # (ptv3.py:264-280) on the tensor cores with hi/lo-split operands (fp32-class results); "exact" = the same numerics from
+        # the SIMT fp32 kernel.  The attribute may be overridden after construction.
+        self.attention_mode = "f16" if enable_flash else "tc32"
         # evaluate the timestep MLP once per scene when the t_emb rows are uniform inside each scene
         # (always true for DefaultSegmentorV2: default.py:400-402, 451-454); False forces the per-point path
         self.t_emb_per_scene = True
         self.overlap_streams = True          # run the Noise Network on a second CUDA stream beside the Conditional Network
+        self.perm_fn = None                  # tests / bench: replaces the CPU torch.randperm draws of shuffle_orders (structure.py:95, ptv3.py:502)
         self.n_cfg = dict(stride=n_stride, enc_depths=n_enc_depths, dec_depths=n_dec_depths)
         self.c_cfg = dict(stride=c_stride, enc_depths=c_enc_depths, dec_depths=c_dec_depths)
         no = len(self.order)
@@ -571,14 +576,14 @@ class PointTransformerV3(nn.Module):
 
     # ------------------------------------------------------------------------------------
     @staticmethod
-    def _run_stage(stage, point, levels, s, exact):
+    def _run_stage(stage, point, levels, s, mode):
         for name, m in stage._modules.items():
             if name == "down":
                 point = m(point, levels[s])
             elif name == "up":
                 point = m(point)
             else:
-                point = m(point, exact)
+                point = m(point, mode)
         return point
 
     def _prep(self, d, level):
@@ -602,10 +607,12 @@ class PointTransformerV3(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("cdsegnet_b200: inputs must be CUDA tensors (no CPU fallback)")
         with ops.stream_scope(torch.cuda.current_stream(dev)):
-            return self._forward(c_point, n_point, perm_fn)
+            return self._forward(c_point, n_point, perm_fn or self.perm_fn)
 
     def _forward(self, c_point, n_point, perm_fn):
-        exact = self.exact_attention
+        exact = self.attention_mode                  # one of ops.ATTN_MODES, handed down to every attention layer
+        if exact not in ops.ATTN_MODES:
+            raise ValueError(f"attention_mode {exact!r} not in {ops.ATTN_MODES}")
         src = n_point
         flags = None
         t_emb = None

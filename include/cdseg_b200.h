@@ -109,6 +109,14 @@ void cdseg_attn_set_poly(int per8);
 int cdseg_attn_tc2(const void* Q, const void* K, const void* V32, const int32_t* patch_len, const int32_t* slot_dst,
                    int H, int T, int Kp, float scale, float* out, int64_t out_ld, void* stream);
 /* exact fp32 SIMT kernel (dense-branch numerics, ptv3.py:264-280) */
+/* third-generation tcgen05 kernel (attn_tc3.cu): P / O double-buffered, O folded one chunk late (no softmax warp ever waits for the
+ * P.V product it just requested).  mode 0: operands of cdseg_attn_pack_f16v(v_ones = 1), flash-branch numerics (fp16 probabilities,
+ * fp16-rounded output).  mode 1: operands of cdseg_attn_pack_split (q / k hi | lo halves, V 48 wide [v_hi | 1 | v_lo]): 22-bit
+ * operands and probabilities, fp32 output -- the dense branch (ptv3.py:264-280) to fp32 accuracy on the tensor cores. */
+int cdseg_attn_pack_split(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src, int H, int T,
+                          int Kp, void* dst0, void* dst1, void* dst2, int has_v, void* stream);
+int cdseg_attn_tc3(const void* Q, const void* K, const void* V, const int32_t* patch_len, const int32_t* slot_dst, int H,
+                   int T, int Kp, float scale, int mode, float* out, int64_t out_ld, void* stream);
 int cdseg_attn_exact(const float* Q, const float* K, const float* V, const int32_t* patch_len,
                      const int32_t* slot_dst, int H, int T, int Kp, float scale, float* out, int64_t out_ld,
                      void* stream);
@@ -190,6 +198,9 @@ int cdseg_conv_tile_plan(const int32_t* nbr, int64_t n, void* plan, void* stream
 void cdseg_set_fused_mask(int mask);
 
 /* ---- native executor of one PTv3 Block (ptv3.py:399-428): the 12-13 launches above enqueued from C++ in one call --- */
+#define CDSEG_ATTN_F16 0
+#define CDSEG_ATTN_EXACT 1
+#define CDSEG_ATTN_TC32 2
 typedef struct CdsegBlockArgs {
   int64_t n; int C, H, T_dim, B;                 /* points, channels, heads (C = 16 H), timestep width, scenes */
   const float* x; const float* conv_in;           /* block input; conv_in != NULL: tensor the CPE conv reads (stale-feature quirk) */
@@ -203,6 +214,8 @@ typedef struct CdsegBlockArgs {
   const float* n1_g; const float* n1_b; const float* qkv_Bp; const float* qkv_b; const float* proj_Bp; const float* proj_b;
   const float* n2_g; const float* n2_b; const float* fc1_Bp; const float* fc1_b; const float* fc2_Bp; const float* fc2_b;
   float ln_eps;
+  int attn_mode;                                  /* CDSEG_ATTN_F16 (flash-branch numerics, tcgen05), CDSEG_ATTN_EXACT (fp32 SIMT, dense-branch
+                                                     numerics) or CDSEG_ATTN_TC32 (tcgen05 with hi/lo-split operands: fp32-class results) */
   float* out; void* scratch; size_t scratch_bytes; /* out [n,C]; scratch >= cdseg_block_scratch_bytes(...) */
   void* ev[6];                                    /* optional cudaEvent_t pairs recorded around: [0,1] the attention kernel, [2,3] the post-attention
                                                      kernel (fc1 GEMM on the unfused path), [4,5] the pre-attention kernel (cpe conv GEMM when unfused) */

@@ -18,6 +18,7 @@ torch.manual_seed(0)
 seg = cb.build_model(configs.segmentor_cfg())
 bench.random_weights(seg)
 seg = seg.to(dev).eval()
+seg.backbone.attention_mode = sys.argv[2] if len(sys.argv) > 2 else "tc32"
 sc = bench.make_scene(0)
 inp = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items()}
 noise = torch.randn(len(sc["coord"]), 6, device=dev)

@@ -1,0 +1,138 @@
+"""Parity of the BENCHMARKED configuration (-m gpu): the full-width CDSegNet of configs/scannet/CDSegNet.py:55-141 (C = 32..512,
+heads 2..32, patch 1024, 37 blocks + TransferModule, 101.4 M parameters) on the 120 000-point synthetic ScanNet scene bench.py
+times, and on a ragged batch of three scenes, through the native block executor (cdseg_block_forward: fused pre / post kernels at
+C <= 128, split-K + reduce_ln branch at C = 256 / 512, attention at H = 16 / 32) -- the code path whose throughput is reported.
+
+Bars (north_star): logits within 1e-3 abs of the fp32 reference forward (oracle dense branch, ptv3.py:264-280) for the fp32-faithful
+attention modes "tc32" (tcgen05, hi/lo-split operands) and "exact" (SIMT); the fp16 flash-branch mode "f16" is held to 8e-3 against
+the oracle's fp16 emulation of ptv3.py:282-289 and must stay inside the reference's own flash-vs-dense gap.  Serialization codes /
+orders / inverses bit-exact (pooling_inverse / idx_ptr of the same scenes: tests/test_gpu_ops.py::test_plan_vs_oracle).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import replay, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _weights(model, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+            m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+
+
+class Case:
+    def __init__(self, scene, seed=5):
+        import cdsegnet_b200 as cb
+        from cdsegnet_b200 import configs
+        from oracle import ptv3_oracle as O
+        self.scene = scene
+        self.cfg = configs.backbone_cfg()
+        torch.manual_seed(0)
+        self.model = cb.PointTransformerV3(**self.cfg)
+        _weights(self.model)
+        self.model = self.model.eval()
+        self.sd = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        n = len(scene["coord"])
+        rng = np.random.default_rng(seed)
+        self.noise = rng.standard_normal((n, 6)).astype(np.float32)
+        self.perms = [rng.permutation(4) for _ in range(8)]
+        self._ref = {}
+        self.O = O
+
+    def oracle(self, mode):
+        if mode not in self._ref:
+            sc = self.scene
+            base = dict(coord=t(sc["coord"]), grid_coord=t(sc["grid_coord"]).long(), offset=t(sc["offset"]))
+            ts = 999 * torch.ones((len(sc["coord"]), 1), dtype=torch.int64)
+            torch.set_num_threads(min(16, torch.get_num_threads()))
+            c, n = self.O.forward(self.sd, self.cfg, dict(base, feat=t(self.noise), t_emb=self.O.calc_t_emb(ts, 128)),
+                                  dict(base, feat=t(sc["feat"])), attn_mode=mode, perm_fn=replay(self.perms))
+            self._ref[mode] = (c["feat"].numpy(), n["feat"].numpy(),
+                               {k: n[k].numpy() for k in ("serialized_code", "serialized_order", "serialized_inverse")})
+        return self._ref[mode]
+
+    def cuda(self, mode):
+        from cdsegnet_b200 import ops
+        from cdsegnet_b200.segmentor import calc_t_emb
+        assert ops.NATIVE_BLOCKS and ops.GEMM_MODE == "tc"
+        m = self.model.to(DEV)
+        m.attention_mode = mode
+        sc = self.scene
+        base = dict(coord=t(sc["coord"]).to(DEV), grid_coord=t(sc["grid_coord"]).to(DEV), offset=t(sc["offset"]).to(DEV))
+        ts = 999 * torch.ones((len(sc["offset"]), 1), dtype=torch.int64, device=DEV)
+        c, n = m(dict(base, feat=t(self.noise).to(DEV), t_emb=calc_t_emb(ts, 128)), dict(base, feat=t(sc["feat"]).to(DEV)),
+                 perm_fn=replay(self.perms))
+        torch.cuda.synchronize()
+        return c, n
+
+
+@pytest.fixture(scope="module")
+def case120k(lib):
+    from cdsegnet_b200 import synth
+    return Case(synth.collate([synth.scannet_scene(120000, 0)]))
+
+
+@pytest.fixture(scope="module")
+def case3x(lib):
+    from cdsegnet_b200 import synth
+    return Case(synth.collate([synth.scannet_scene(n, 3 + i, room_m=(5.0, 4.0, 3.0), n_boxes=5) for i, n in enumerate((40000, 33000, 900))]))
+
+
+def _check_fp32(case, mode):
+    c_ref, n_ref, ser = case.oracle("dense")
+    c, n = case.cuda(mode)
+    en = float(np.abs(n["feat"].cpu().numpy() - n_ref).max())
+    ec = float(np.abs(c["feat"].cpu().numpy() - c_ref).max())
+    print(f"full width, attention {mode}: max|logit - oracle| = {en:.3e} (CN), {ec:.3e} (NN); |logit| max {np.abs(n_ref).max():.2f}")
+    assert en < 1e-3 and ec < 1e-3
+    for key, ref in ser.items():
+        assert np.array_equal(n[key].cpu().numpy(), ref), key
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("mode", ["tc32", "exact"])
+def test_full_width_120k_scene_fp32_modes(case120k, mode):
+    _check_fp32(case120k, mode)
+
+
+@pytest.mark.timeout(900)
+def test_full_width_120k_scene_f16_mode(case120k):
+    _, n_ref, _ = case120k.oracle("dense")
+    _, n16, _ = case120k.oracle("flash16")
+    _, n = case120k.cuda("f16")
+    got = n["feat"].cpu().numpy()
+    gap = float(np.abs(n16 - n_ref).max())
+    e16, e32 = float(np.abs(got - n16).max()), float(np.abs(got - n_ref).max())
+    print(f"full width, attention f16: vs flash16 emulation {e16:.3e}, vs dense {e32:.3e}; emulation-vs-dense gap {gap:.3e}")
+    assert e16 < 8e-3
+    assert e32 < max(2e-2, 2 * gap)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("mode", ["tc32", "exact"])
+def test_full_width_ragged_batch_fp32_modes(case3x, mode):
+    """three scenes of 40 000 / 33 000 / 900 points: multi-scene patch maps, a scene smaller than a patch, per-scene timestep rows"""
+    _check_fp32(case3x, mode)
+
+
+@pytest.mark.timeout(900)
+def test_full_width_segmentor_entry_point(case120k):
+    """the call bench.py times: DefaultSegmentorV2.inference on the shipped config with the fp32-faithful attention"""
+    import cdsegnet_b200 as cb
+    from cdsegnet_b200 import configs
+    _, n_ref, _ = case120k.oracle("dense")
+    seg = cb.build_model(configs.segmentor_cfg())
+    seg.backbone.load_state_dict(case120k.sd, strict=True)
+    seg = seg.to(DEV).eval()
+    seg.backbone.attention_mode = "tc32"
+    sc = case120k.scene
+    inp = {k: t(sc[k]).to(DEV) for k in ("coord", "grid_coord", "offset", "feat")}
+    seg.backbone.perm_fn = replay(case120k.perms)
+    out = seg.inference(inp, eval=False, noise=t(case120k.noise))["seg_logits"]
+    assert float(np.abs(out.cpu().numpy() - n_ref).max()) < 1e-3

@@ -11,12 +11,16 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def run_cuda(z, cfg, shapes, exact, perms=None, seed=None):
+def run_cuda(z, cfg, shapes, exact, perms=None, seed=None, mode=None):
+    """exact: enable_flash=False (the reference's dense fp32 branch; here the tcgen05 "tc32" attention unless `mode` says otherwise)"""
     import cdsegnet_b200 as cb
     cfg = dict(cfg, enable_flash=not exact)
     m = cb.PointTransformerV3(**cfg)
     m.load_state_dict(synth_state_dict(shapes), strict=True)
     m = m.to(DEV).eval()
+    assert m.attention_mode == ("tc32" if exact else "f16")
+    if mode is not None:
+        m.attention_mode = mode
     base = dict(coord=t(z["coord"]).to(DEV), grid_coord=t(z["grid_coord"]).to(DEV), offset=t(z["offset"]).to(DEV))
     pf = None
     if seed is not None:
@@ -36,12 +40,13 @@ def run_cuda(z, cfg, shapes, exact, perms=None, seed=None):
     return None, nn_, m
 
 
+@pytest.mark.parametrize("mode", ["tc32", "exact"])
 @pytest.mark.parametrize("name", ["case3_cn_only", "case1_single", "case2_batch2"])
-def test_exact_mode_matches_reference_logits(name):
-    """fp32 path (exact attention): logits within 1e-3 abs of the REFERENCE forward (north_star tolerance);
-    serialization indices bit-exact."""
+def test_exact_mode_matches_reference_logits(name, mode):
+    """fp32 path (enable_flash=False: tcgen05 attention with hi/lo-split operands, or the SIMT fp32 kernel): logits within 1e-3 abs
+    of the REFERENCE forward (north_star tolerance); serialization indices bit-exact."""
     z, cfg, shapes = load_case(name)
-    c, n, _ = run_cuda(z, cfg, shapes, exact=True)
+    c, n, _ = run_cuda(z, cfg, shapes, exact=True, mode=mode)
     assert np.abs(n["feat"].cpu().numpy() - z["n_feat"]).max() < 1e-3
     if c is not None:
         assert np.abs(c["feat"].cpu().numpy() - z["c_feat"]).max() < 1e-3

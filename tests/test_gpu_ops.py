@@ -61,12 +61,21 @@ def _scene(counts, seed=0):
     return synth.collate([synth.small_room(c, seed + i) for i, c in enumerate(counts)])
 
 
-@pytest.mark.parametrize("counts", [(2000,), (1500, 700, 1100)])
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("counts", [(2000,), (1500, 700, 1100), "scannet120k", "scannet3x"])
 def test_plan_vs_oracle(ops, counts):
     """serialization + the whole pooling hierarchy (CN strides 2,2,2,2 / NN strides 4,4) bit-exact,
-    including the reference's shuffle bookkeeping"""
+    including the reference's shuffle bookkeeping -- small rooms, the benchmarked 120k-point scene (BASELINE config 2) and a ragged
+    batch of three ScanNet-shaped scenes"""
     from cdsegnet_b200.structure import Plan
-    sc = _scene(counts)
+    from cdsegnet_b200 import synth
+    if counts == "scannet120k":
+        sc = synth.collate([synth.scannet_scene(120000, 0)])
+    elif counts == "scannet3x":
+        sc = synth.collate([synth.scannet_scene(n, 3 + i, room_m=(5.0, 4.0, 3.0), n_boxes=5) for i, n in enumerate((40000, 33000, 900))])
+    else:
+        sc = _scene(counts)
+    counts = np.diff(sc["offset"], prepend=0)
     rng = np.random.default_rng(7)
     perms = [rng.permutation(4) for _ in range(8)]
     it = iter(perms)
@@ -221,7 +230,9 @@ def test_small_linear_and_scale_shift(ops):
     assert int(flag.item()) == 1
 
 
-def _attn_case(ops, counts, K, H, exact, seed=0):
+def _attn_case(ops, counts, K, H, mode, seed=0, oracle_mode=None):
+    """mode: ops.ATTN_MODES.  The reference is the oracle's dense fp32 formula ("tc32", "exact") or its fp16 emulation of the
+    flash branch ("f16") on the same gathered rows (ptv3.py:258-290)."""
     n, C = sum(counts), H * 16
     gen = torch.Generator().manual_seed(seed)
     qkv = torch.randn(n, 3 * C, generator=gen) * 1.5
@@ -229,41 +240,67 @@ def _attn_case(ops, counts, K, H, exact, seed=0):
     pad, unpad, cu_seq = S.patch_maps(np.cumsum(counts), K)
     inv = np.empty(n, np.int64); inv[order] = np.arange(n)
     g = qkv[torch.from_numpy(order[pad])]
-    mode = "dense" if exact else "flash16"
-    ref = O.varlen_attention(g[:, :C], g[:, C:2 * C], g[:, 2 * C:], cu_seq, H, 0.25, mode)[torch.from_numpy(unpad[inv])]
+    omode = oracle_mode or ("flash16" if mode == "f16" else "dense")
+    ref = O.varlen_attention(g[:, :C], g[:, C:2 * C], g[:, 2 * C:], cu_seq, H, 0.25, omode)[torch.from_numpy(unpad[inv])]
     pm = ops.patch_maps(cu(order.astype(np.int32)), np.array(counts), K)
-    q, k, v = ops.attn_pack(qkv.to(DEV), 0, C, 3, pm, H, exact)
-    out = ops.attn(q, k, v, pm, H, 0.25, n, exact)
+    q, k, v = ops.attn_pack(qkv.to(DEV), 0, C, 3, pm, H, mode)
+    out = ops.attn(q, k, v, pm, H, 0.25, n, mode)
     torch.cuda.synchronize()
     return out.cpu(), ref
 
 
-@pytest.mark.parametrize("counts,K,H", [((300,), 128, 2), ((1000, 77, 129), 128, 4), ((64,), 64, 1), ((2500,), 1024, 2),
-                                         ((991,), 1024, 8), ((40, 900), 256, 3)])
+# shapes: short / ragged / sub-patch scenes, the 2500- and 5000-point multi-patch cases, and the deep levels of the shipped config
+# (H = 16 at 3 804 points, H = 32 at one unpadded 991-point sequence: SURVEY.md App. B "stage/patch geometry")
+ATTN_SHAPES = [((128,), 128, 1), ((300,), 128, 2), ((1000, 77, 129), 128, 4), ((64,), 64, 1), ((2500,), 1024, 2), ((991,), 1024, 8),
+               ((40, 900), 256, 3), ((5000,), 1024, 4), ((3804,), 1024, 16), ((991,), 1024, 32), ((991, 1030), 1024, 32)]
+
+
+@pytest.mark.parametrize("counts,K,H", ATTN_SHAPES)
 def test_attention_exact_vs_dense_oracle(ops, counts, K, H):
-    out, ref = _attn_case(ops, counts, K, H, exact=True)
+    out, ref = _attn_case(ops, counts, K, H, "exact")
     assert (out - ref).abs().max() < 2e-5          # fp32 both sides
 
 
 @pytest.mark.timeout(120)
+@pytest.mark.parametrize("counts,K,H", ATTN_SHAPES)
+def test_attention_tc32_vs_dense_oracle(ops, counts, K, H):
+    """tcgen05 kernel with hi/lo-split operands and probabilities (cdseg_attn_tc3 mode 1) against the dense fp32 formula
+    (ptv3.py:264-280): 22-bit operands + ex2.approx leave ~1e-6 relative; 2e-5 abs on outputs of magnitude ~1"""
+    out, ref = _attn_case(ops, counts, K, H, "tc32")
+    assert (out - ref).abs().max() < 2e-5
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("gen", [1, 2])
 @pytest.mark.parametrize("counts,K,H", [((300,), 128, 2), ((1000, 77, 129), 128, 4), ((2500,), 1024, 2), ((5000,), 1024, 4)])
-def test_attention_tcgen05_v1_kernel_still_correct(ops, counts, K, H):
-    """the first-generation kernel (whole-patch K/V image) stays in the library"""
-    ops.ATTN_V2 = False
+def test_attention_tcgen05_older_kernels_still_correct(ops, counts, K, H, gen):
+    """the first- (whole-patch K/V image) and second-generation (K/V ring) kernels stay in the library as A/B comparators"""
+    ops.ATTN_KERNEL = gen
     try:
-        out, ref = _attn_case(ops, counts, K, H, exact=False)
+        out, ref = _attn_case(ops, counts, K, H, "f16")
     finally:
-        ops.ATTN_V2 = True
+        ops.ATTN_KERNEL = 3
     assert (out - ref).abs().max() < 2e-3
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("counts,K,H", [((128,), 128, 1), ((300,), 128, 2), ((1000, 77, 129), 128, 4), ((64,), 64, 1),
-                                         ((2500,), 1024, 2), ((991,), 1024, 8), ((40, 900), 256, 3), ((5000,), 1024, 4)])
+@pytest.mark.parametrize("counts,K,H", ATTN_SHAPES)
 def test_attention_tcgen05_vs_flash_oracle(ops, counts, K, H):
     """fp16 operands / fp32 accumulate / fp16 probabilities, like flash_attn: tolerance 2e-3 abs on
     outputs of magnitude ~1 (fp16 rounding of P and of the reference's fp16 output)"""
-    out, ref = _attn_case(ops, counts, K, H, exact=False)
+    out, ref = _attn_case(ops, counts, K, H, "f16")
+    assert (out - ref).abs().max() < 2e-3
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("poly", [1, 3])
+def test_attention_fma_pipe_exponentials(ops, lib, poly):
+    """1 / 3 of every 8 exponentials evaluated by the FMA-pipe polynomial (cdseg_attn_set_poly): same bar as the MUFU path"""
+    lib.cdseg_attn_set_poly(poly)
+    try:
+        out, ref = _attn_case(ops, (2500,), 1024, 2, "f16")
+    finally:
+        lib.cdseg_attn_set_poly(0)
     assert (out - ref).abs().max() < 2e-3
 
 
@@ -284,8 +321,8 @@ def test_attention_tcgen05_vs_real_flash_attn(ops, counts, K, H):
     ref = fa.flash_attn_varlen_qkvpacked_func(g.half().reshape(-1, 3, H, 16), cu(cu_seq), max_seqlen=K, dropout_p=0,
                                               softmax_scale=0.25).reshape(-1, C).float()[cu(unpad[inv])]
     pm = ops.patch_maps(cu(order.astype(np.int32)), np.array(counts), K)
-    q, k, v = ops.attn_pack(qkv.to(DEV), 0, C, 3, pm, H, False)
-    out = ops.attn(q, k, v, pm, H, 0.25, n, False)
+    q, k, v = ops.attn_pack(qkv.to(DEV), 0, C, 3, pm, H, "f16")
+    out = ops.attn(q, k, v, pm, H, 0.25, n, "f16")
     d = (out - ref).abs()
     assert (d <= 2.0 ** -10 * ref.abs().clamp(min=0.5)).all().item()      # <= 1 fp16 ulp
     assert d.mean().item() < 5e-5

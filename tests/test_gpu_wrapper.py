@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from helpers import t
+from helpers import load_case, replay, t
 from oracle import wrapper_oracle as W
 from oracle.weights import synth_state_dict
 
@@ -190,3 +190,34 @@ def test_fused_adamw_vs_torch_and_param_groups():
     torch.cuda.synchronize()
     worst = max(float((p.detach().cpu() - ref[n]).abs().max()) for n, p in m.named_parameters())
     assert worst < 2e-6, worst
+
+
+def test_optimizer_step_invalidates_packed_weight_caches():
+    """FusedAdamW writes parameters through raw pointers; the forward's packed tensor-core operand caches are keyed on
+    Parameter._version, so a step must bump it: step -> forward must equal the forward of a freshly built model holding the
+    updated weights (stale packed weights after optimizer.step())."""
+    import copy
+    import cdsegnet_b200 as cb
+    from cdsegnet_b200.optim import build_optimizer
+    z, cfg, shapes = load_case("case3_cn_only")
+    m = cb.PointTransformerV3(**dict(cfg, enable_flash=False))
+    m.load_state_dict(synth_state_dict(shapes), strict=True)
+    m = m.to(DEV).eval()
+    base = dict(coord=t(z["coord"]).to(DEV), grid_coord=t(z["grid_coord"]).to(DEV), offset=t(z["offset"]).to(DEV))
+
+    def fwd(model):
+        out = model(n_point=dict(base, feat=t(z["feat"]).to(DEV)), perm_fn=replay(z["perms"]))["feat"]
+        torch.cuda.synchronize()
+        return out.cpu().numpy()
+    before = fwd(m)                                       # fills the pack caches
+    opt = build_optimizer(dict(type="AdamW", lr=0.05, weight_decay=0.0), m, [dict(keyword="block", lr=0.02)])
+    g = torch.Generator().manual_seed(3)
+    for p in m.parameters():
+        p.grad = torch.randn(p.shape, generator=g).to(DEV)
+    opt.step()
+    after = fwd(m)
+    fresh = cb.PointTransformerV3(**dict(cfg, enable_flash=False))
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in m.state_dict().items()}, strict=True)
+    ref = fwd(fresh.to(DEV).eval())
+    assert np.abs(after - before).max() > 1e-2            # the step changed the network ...
+    assert np.abs(after - ref).max() < 1e-5               # ... and the forward saw the new weights
