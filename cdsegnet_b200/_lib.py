@@ -106,6 +106,7 @@ SIGNATURES = {
     "cdseg_attn_tc_smem_bytes": (_Z, [_I]),
     "cdseg_attn_tc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
     "cdseg_attn_pack_split": (_I, [_P, _L, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "cdseg_attn_set_debug": (None, [_I]),
     "cdseg_attn_tc3": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P, _L, _P]),
     "cdseg_attn_exact": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _L, _P]),
     "cdseg_add_layernorm": (_I, [_P, _P, _P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),

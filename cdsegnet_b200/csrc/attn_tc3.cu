@@ -153,7 +153,9 @@ template <int R> struct Bars {
   uint32_t tmem_slot, pad;
 };
 
-template <int MODE, int POLY>      // POLY of every 8 exponentials go to the FMA pipe (0 = all on MUFU); MODE 1 always uses MUFU
+// DBG != 0: what-if variants for profiling ONLY (wrong results, selected by cdseg_attn_set_debug, never by the product path):
+// 1 no exponentials, 2 S read from tensor memory only for the first chunk, 3 no P stores, 4 no row max, 5 no P.V MMAs, 6 no O fold loads
+template <int MODE, int POLY, int DBG = 0>      // POLY of every 8 exponentials go to the FMA pipe (0 = all on MUFU); MODE 1 always uses MUFU
 __global__ void __launch_bounds__(NTHREADS, MODE == 0 ? 3 : 2)
 attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, const __half* __restrict__ Vp,
                 const int32_t* __restrict__ patch_len, const int32_t* __restrict__ slot_dst, int H, int T, int Kp, float sl2,
@@ -251,7 +253,7 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
           const uint32_t od = tmem + (b ? C::COL_O1 : C::COL_O0);
 #pragma unroll
           for (int kk = 0; kk < NC / 16; ++kk)
-            umma_f16(od, make_desc(pb + kk * 2 * 2048, 2048, 128), make_desc(vb + kk * 2 * VKG, VKG, 128), IDESC_O, kk > 0);
+            if (DBG != 5 || gp == 0) umma_f16(od, make_desc(pb + kk * 2 * 2048, 2048, 128), make_desc(vb + kk * 2 * VKG, VKG, 128), IDESC_O, kk > 0);
           if (MODE == 1) {
 #pragma unroll
             for (int kk = 0; kk < NC / 16; ++kk)
@@ -279,9 +281,14 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
       const uint32_t oc = tmem + lane_base + (b ? C::COL_O1 : C::COL_O0);
       if (MODE == 0) {
         uint32_t o[17];
-        tmem_ld16(oc, o);
-        tmem_ld1(oc + 16, o + 16);
-        tmem_ld_wait();
+        if (DBG == 6 && gp > 0) {
+#pragma unroll
+          for (int d = 0; d < 17; ++d) o[d] = 0x3f800000u;
+        } else {
+          tmem_ld16(oc, o);
+          tmem_ld1(oc + 16, o + 16);
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int d = 0; d < 16; ++d) acc[d] = fmaf(acc[d], a, __uint_as_float(o[d]));
         l = fmaf(l, a, __uint_as_float(o[16]));
@@ -301,9 +308,14 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
       mbar_wait(smem_u32(&bars->s_full), (uint32_t)(g & 1));
       tc_fence_after();
       uint32_t s[NC];
-      tmem_ld32(tmem + lane_base + C::COL_S, s);
-      tmem_ld32(tmem + lane_base + C::COL_S + 32, s + 32);
-      tmem_ld_wait();
+      if (DBG == 2 && g > 0) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) s[j] = __float_as_uint((float)(j + g) * 0.01f);
+      } else {
+        tmem_ld32(tmem + lane_base + C::COL_S, s);
+        tmem_ld32(tmem + lane_base + C::COL_S + 32, s + 32);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->s_free));                      // S lives in registers now: the next QK^T may start
       const int valid = len - g * NC;                            // keys >= valid are padding
@@ -313,8 +325,11 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
         for (int j = 0; j < NC; ++j)
           if (j >= valid) s[j] = 0xff800000u;                    // -inf
       }
+      if (DBG == 4) mx = __uint_as_float(s[0]);
+      else {
 #pragma unroll
-      for (int j = 0; j < NC; j += 2) mx = max3(mx, __uint_as_float(s[j]), __uint_as_float(s[j + 1]));
+        for (int j = 0; j < NC; j += 2) mx = max3(mx, __uint_as_float(s[j]), __uint_as_float(s[j + 1]));
+      }
       const float m_new = fmaxf(m, mx);
       const float msc = m_new * sl2;
       const float a_g = ex2(m * sl2 - msc);                      // first chunk: m = -inf -> 0
@@ -327,8 +342,8 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float x0 = fmaf(__uint_as_float(s[kg * 8 + 2 * j]), sl2, -msc), x1 = fmaf(__uint_as_float(s[kg * 8 + 2 * j + 1]), sl2, -msc);
-          const float p0 = (MODE == 0 && 2 * j < POLY) ? ex2_fma(x0) : ex2(x0);
-          const float p1 = (MODE == 0 && 2 * j + 1 < POLY) ? ex2_fma(x1) : ex2(x1);
+          const float p0 = DBG == 1 ? x0 : ((MODE == 0 && 2 * j < POLY) ? ex2_fma(x0) : ex2(x0));
+          const float p1 = DBG == 1 ? x1 : ((MODE == 0 && 2 * j + 1 < POLY) ? ex2_fma(x1) : ex2(x1));
           __half2 hh = __floats2half2_rn(p0, p1);
           pk[j] = *reinterpret_cast<uint32_t*>(&hh);
           if (MODE == 1) {
@@ -337,7 +352,8 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
             pl[j] = *reinterpret_cast<uint32_t*>(&ll);
           }
         }
-        *reinterpret_cast<uint4*>(pw + kg * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (DBG != 3) *reinterpret_cast<uint4*>(pw + kg * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        else if (kg == 0) *reinterpret_cast<uint4*>(pw) = make_uint4(pk[0] ^ pk[1], pk[2] ^ pk[3], 0, 0);
         if (MODE == 1) *reinterpret_cast<uint4*>(pw + 128 * NC * 2 + kg * 2048) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
       }
       fence_async_smem();                                        // generic-proxy writes -> visible to the tensor core
@@ -378,6 +394,8 @@ template <int MODE> constexpr size_t smem_bytes() {
 }  // namespace tc3
 
 // exponentials per group of 8 computed on the FMA pipe instead of MUFU (0..3), MODE 0 only; env CDSEG_ATTN_POLY or cdseg_attn_set_poly
+static int g_attn3_debug = 0;
+CDSEG_API void cdseg_attn_set_debug(int variant) { g_attn3_debug = variant; }
 int g_cdseg_attn_poly = [] { const char* e = getenv("CDSEG_ATTN_POLY"); return e ? atoi(e) : 0; }();
 CDSEG_API void cdseg_attn_set_poly(int per8) { g_cdseg_attn_poly = per8 < 0 ? 0 : (per8 > 3 ? 3 : per8); }
 
@@ -397,6 +415,11 @@ CDSEG_API int cdseg_attn_tc3(const void* Q, const void* K, const void* V, const 
   if (e != cudaSuccess) return (int)e;
     CDSEG_SET(0, 0) CDSEG_SET(0, 1) CDSEG_SET(0, 2) CDSEG_SET(0, 3) CDSEG_SET(1, 0)
 #undef CDSEG_SET
+#define CDSEG_SETD(D)                                                                                                      \
+  e = cudaFuncSetAttribute(tc3::attn_tc3_kernel<0, 0, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc3::smem_bytes<0>()); \
+  if (e != cudaSuccess) return (int)e;
+    CDSEG_SETD(1) CDSEG_SETD(2) CDSEG_SETD(3) CDSEG_SETD(4) CDSEG_SETD(5) CDSEG_SETD(6)
+#undef CDSEG_SETD
     init = true;
   }
   dim3 g(Kp / 128, T, H);
@@ -404,6 +427,19 @@ CDSEG_API int cdseg_attn_tc3(const void* Q, const void* K, const void* V, const 
 #define CDSEG_ATTN_LAUNCH(MODE, POLY)                                                                                      \
   tc3::attn_tc3_kernel<MODE, POLY><<<g, tc3::NTHREADS, tc3::smem_bytes<MODE>(), (cudaStream_t)stream>>>(                   \
       (const __half*)Q, (const __half*)K, (const __half*)V, patch_len, slot_dst, H, T, Kp, sl2, out, out_ld)
+#define CDSEG_ATTN_LAUNCH_D(D)                                                                                             \
+  tc3::attn_tc3_kernel<0, 0, D><<<g, tc3::NTHREADS, tc3::smem_bytes<0>(), (cudaStream_t)stream>>>(                         \
+      (const __half*)Q, (const __half*)K, (const __half*)V, patch_len, slot_dst, H, T, Kp, sl2, out, out_ld)
+  if (mode == 0 && g_attn3_debug) {
+    switch (g_attn3_debug) {
+      case 1: CDSEG_ATTN_LAUNCH_D(1); break;
+      case 2: CDSEG_ATTN_LAUNCH_D(2); break;
+      case 3: CDSEG_ATTN_LAUNCH_D(3); break;
+      case 4: CDSEG_ATTN_LAUNCH_D(4); break;
+      case 5: CDSEG_ATTN_LAUNCH_D(5); break;
+      default: CDSEG_ATTN_LAUNCH_D(6); break;
+    }
+  } else
   if (mode == 1) CDSEG_ATTN_LAUNCH(1, 0);
   else if (g_cdseg_attn_poly == 1) CDSEG_ATTN_LAUNCH(0, 1);
   else if (g_cdseg_attn_poly == 2) CDSEG_ATTN_LAUNCH(0, 2);

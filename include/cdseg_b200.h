@@ -115,6 +115,8 @@ int cdseg_attn_tc2(const void* Q, const void* K, const void* V32, const int32_t*
  * operands and probabilities, fp32 output -- the dense branch (ptv3.py:264-280) to fp32 accuracy on the tensor cores. */
 int cdseg_attn_pack_split(const float* src, int64_t ld, int col0, int C, int nwhich, const int32_t* slot_src, int H, int T,
                           int Kp, void* dst0, void* dst1, void* dst2, int has_v, void* stream);
+/* profiling only: what-if variants of the mode-0 kernel that drop one piece of work each (results are WRONG): 0 = off */
+void cdseg_attn_set_debug(int variant);
 int cdseg_attn_tc3(const void* Q, const void* K, const void* V, const int32_t* patch_len, const int32_t* slot_dst, int H,
                    int T, int Kp, float scale, int mode, float* out, int64_t out_ld, void* stream);
 int cdseg_attn_exact(const float* Q, const float* K, const float* V, const int32_t* patch_len,
