@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
-SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "attn_tc3.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "losses.cu", "fragments.cu", "knn.cu"]
+SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "attn_tc3.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "plan_exec.cu", "net_exec.cu", "losses.cu", "fragments.cu", "knn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]
 
@@ -75,6 +75,26 @@ class BlockArgs(ctypes.Structure):
                 ("ln_eps", _F), ("attn_mode", _I), ("out", _P), ("scratch", _P), ("scratch_bytes", _Z), ("ev", _P * 6)]
 
 
+MAX_SCENES = 64
+
+
+class PatchMap(ctypes.Structure):
+    """mirror of CdsegPatchMap"""
+    _fields_ = [("slot_src", _P), ("slot_dst", _P), ("point_slot", _P), ("patch_len", _P), ("T", _I), ("Kp", _I), ("K", _I), ("pad_", _I),
+                ("pairs", _L)]
+
+
+class PlanLevel(ctypes.Structure):
+    """mirror of CdsegPlanLevel"""
+    _fields_ = [("parent", _I), ("stride", _I), ("rowmap", _I * 4), ("K", _I), ("pm_mask", ctypes.c_uint), ("want_conv_plan", _I),
+                ("stem_ksize", _I), ("n", _L), ("cap", _L), ("B", _I), ("depth", _I), ("c0", _I), ("pooling_depth", _I), ("slot", _I),
+                ("pad_", _I), ("offset_host", _L * MAX_SCENES),
+                ("grid", _P), ("batch", _P), ("code", _P), ("order", _P), ("inverse", _P),
+                ("cluster", _P), ("idx_ptr", _P), ("head", _P), ("m_dev", _P), ("offset_dev", _P),
+                ("perm", _P), ("inv_perm", _P), ("o_code", _P), ("o_order", _P), ("o_inverse", _P),
+                ("nbr3", _P), ("tile_mask3", _P), ("conv_plan3", _P), ("nbr_stem", _P), ("pm", PatchMap * 4)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/cdseg_b200.h
 SIGNATURES = {
     "cdseg_abi_version": (_I, []),
@@ -125,6 +145,12 @@ SIGNATURES = {
     "cdseg_pre_attn_set_trace": (None, [_P, _I]),
     "cdseg_conv_plan_bytes": (_Z, [_L]),
     "cdseg_conv_tile_plan": (_I, [_P, _L, _P, _P]),
+    "cdseg_plan_arena_bytes": (_Z, [_L, _I, _I, _I, _I, _I, _I, _I]),
+    "cdseg_plan_build": (_I, [_P, _P, _L, _I, ctypes.POINTER(_I), _I, ctypes.POINTER(PlanLevel), _I, _P, _I, ctypes.POINTER(ctypes.c_int32), _P, _Z, _P]),
+    "cdseg_net_arena_bytes": (_I, [_P, ctypes.POINTER(_Z), ctypes.POINTER(_Z)]),
+    "cdseg_net_forward": (_I, [_P]),
+    "cdseg_struct_sizes": (_I, [ctypes.POINTER(_Z), _I]),
+    "cdseg_gather_rows_pad": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "cdseg_set_fused_mask": (None, [_I]),
     "cdseg_block_scratch_bytes": (_Z, [_L, _I, _I, _I, _I, _I]),
     "cdseg_block_forward": (_I, [ctypes.POINTER(BlockArgs), _P]),

@@ -446,6 +446,25 @@ __global__ void renumber_kernel(const int32_t* __restrict__ perm, const int32_t*
   }
 }
 
+// dst[i, 0..C) = src[idx[i], 0..C), dst[i, C..Cp) = 0: the stem's input rows in internal numbering, zero-padded to the 8 channels the
+// im2col GEMM consumes (replaces feat[perm] + F.pad in front of cdseg_conv_im2col_tc)
+__global__ void gather_rows_pad_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, int C, int Cp,
+                                       float* __restrict__ dst) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n * Cp) return;
+  const int64_t r = t / Cp;
+  const int c = (int)(t % Cp);
+  dst[t] = c < C ? src[(int64_t)idx[r] * C + c] : 0.f;
+}
+CDSEG_API int cdseg_gather_rows_pad(const float* src, const int32_t* idx, int64_t n, int C, int Cp, float* dst, void* stream) {
+  if (n < 0 || C <= 0 || Cp < C || !src || !idx || !dst) return CDSEG_EINVAL;
+  if (n == 0) return CDSEG_OK;
+  gather_rows_pad_kernel<<<cdseg_div_up(n * Cp, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, C, Cp, dst);
+  CDSEG_COUNT_LAUNCH(1);
+  CDSEG_LAUNCH_CHECK();
+  return CDSEG_OK;
+}
+
 CDSEG_API int cdseg_renumber(const int32_t* perm, const int32_t* inv_perm, const int32_t* grid, const int32_t* batch, const int64_t* code,
                              const int32_t* order, const int32_t* inverse, int k, int64_t N, int32_t* i_grid, int32_t* i_batch,
                              int64_t* i_code, int32_t* i_order, int32_t* i_inverse, void* stream) {

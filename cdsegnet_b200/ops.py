@@ -374,6 +374,7 @@ def set_fused_mask(mask):
 
 GEMM_MODE = "tc"      # "tc": tcgen05 split-fp16 kernels for conv + linears ; "simt": round-1a SIMT conv + cuBLAS SGEMM
 NATIVE_BLOCKS = True  # run each PTv3 Block through the C++ executor (cdseg_block_forward) instead of launch-by-launch
+NATIVE_NET = True     # run the whole feature phase through ONE C-ABI call (cdseg_net_forward, csrc/net_exec.cu); False: per-module calls
 
 _ARENAS = {}
 

@@ -145,24 +145,29 @@ def packed_linear(w, b=None):
     return _PACK.get((id(w), "packed"), [w, b], build)
 
 
+def packed_folded(w, b=None, bn=None, cols=None):
+    """(packed operand blocks, fp32 bias or None) of y = bn(x @ w[:, cols]^T + b): eval-mode BatchNorm folded into weight / bias; cached"""
+    def build():
+        wf = w.detach().float()
+        if cols is not None:
+            wf = wf[:, cols[0]:cols[1]]
+        bf = b.detach().float() if b is not None else None
+        if bn is not None:
+            sc, sh = bn_fold(bn)
+            wf = wf * sc[:, None]
+            bf = (bf * sc + sh) if bf is not None else sh
+        return ops.gemm_pack_b(wf.t().contiguous()[None]), (bf.contiguous() if bf is not None else None)
+    srcs = [w, b] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
+    return _PACK.get((id(w), cols), srcs, build)
+
+
 def linear(x, w, b=None, act=0, res=None, bn=None, cols=None):
     """act(bn(x @ w[:, cols]^T + b)) + res.  tcgen05 3xTF32 GEMM with everything fused in the epilogue
     (eval-mode BatchNorm is folded into the packed weight/bias); cuBLAS SGEMM path for ops.GEMM_MODE == "simt"."""
     K = x.shape[1]
     N = w.shape[0]
     if ops.GEMM_MODE == "tc" and K % 16 == 0:
-        def build():
-            wf = w.detach().float()
-            if cols is not None:
-                wf = wf[:, cols[0]:cols[1]]
-            bf = b.detach().float() if b is not None else None
-            if bn is not None:
-                sc, sh = bn_fold(bn)
-                wf = wf * sc[:, None]
-                bf = (bf * sc + sh) if bf is not None else sh
-            return ops.gemm_pack_b(wf.t().contiguous()[None]), (bf.contiguous() if bf is not None else None)
-        srcs = [w, b] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [])
-        Bp, bias = _PACK.get((id(w), cols), srcs, build)
+        Bp, bias = packed_folded(w, b, bn, cols)
         M = x.shape[0]
         tiles = -(-M // 128) * -(-N // 128)
         T = 1
@@ -384,20 +389,27 @@ class Embedding(nn.Module):
         super().__init__()
         self.stem = Seq(conv=SubMConv3d(cin, cout, 5, bias=False), norm=_bn(cout), act=nn.GELU())
 
+    def packed(self):
+        """(packed im2col operand with the BatchNorm scale folded in, BatchNorm shift): K = 4 taps x 8 (zero-padded) channels per step"""
+        conv, bn = self.stem.conv, self.stem.norm
+        scale, shift = bn_fold(bn)
+
+        def build():
+            k3 = conv.k ** 3
+            w = conv.wt() * scale                                      # [k3, cin, cout]
+            wp = w.new_zeros((-(-k3 // 4) * 4, 8, conv.cout))
+            wp[:k3, : conv.cin] = w
+            return ops.gemm_pack_b(wp.reshape(-1, 32, conv.cout))
+        Bp = _PACK.get((id(conv.weight), "stem"), [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var], build)
+        return Bp, shift
+
     def forward(self, point):
         level = point["_level"]
         scale, shift = bn_fold(self.stem.norm)
         conv = self.stem.conv
         if conv.cin <= 8 and ops.GEMM_MODE == "tc":
-            # im2col GEMM on the tensor cores: K = 4 taps x 8 (zero-padded) channels per step, BN folded into W / bias
-            def build():
-                k3 = conv.k ** 3
-                w = conv.wt() * scale                                      # [k3, cin, cout]
-                wp = w.new_zeros((-(-k3 // 4) * 4, 8, conv.cout))
-                wp[:k3, : conv.cin] = w
-                return ops.gemm_pack_b(wp.reshape(-1, 32, conv.cout))
-            bn = self.stem.norm
-            Bp = _PACK.get((id(conv.weight), "stem"), [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var], build)
+            # im2col GEMM on the tensor cores, BN folded into W / bias
+            Bp, shift = self.packed()
             x8 = F.pad(point["feat"].float(), (0, 8 - conv.cin))
             point["feat"] = ops.conv_im2col_tc(x8, level.nbr(conv.k), Bp, conv.cout, shift, 1)
         elif conv.cin <= 8:
@@ -525,6 +537,28 @@ class PointTransformerV3(nn.Module):
         self.c_cfg = dict(stride=c_stride, enc_depths=c_enc_depths, dec_depths=c_dec_depths)
         no = len(self.order)
 
+        def level_spec(enc_depths, enc_ch, enc_patch, dec_depths, dec_ch, extra_mask_last=0):
+            """what the plan call must prebuild per level: patch size (the first one used at a level sticks, like the reference's
+            cached pad maps), the logical curves its blocks attend along, whether a fused pre-attention kernel runs there"""
+            out = []
+            for s in range(len(enc_depths)):
+                mask = 0
+                for i in range(enc_depths[s]):
+                    mask |= 1 << (i % no)
+                chans = [enc_ch[s]]
+                if s < len(dec_depths):
+                    for i in range(dec_depths[s]):
+                        mask |= 1 << (i % no)
+                    chans.append(dec_ch[s])
+                if s == len(enc_depths) - 1:
+                    mask |= extra_mask_last
+                out.append(dict(K=enc_patch[s], mask=mask, conv_plan=any(c in (32, 64, 128) for c in chans), stem=5 if s == 0 else 0))
+            return out
+        self.plan_spec = dict(n=level_spec(n_enc_depths, n_enc_channels, n_enc_patch_size, n_dec_depths, n_dec_channels,
+                                           1 if condition else 0))            # TransferModule attends along curve 0 of the last CN level
+        if condition:
+            self.plan_spec["c"] = level_spec(c_enc_depths, c_enc_channels, c_enc_patch_size, c_dec_depths, c_dec_channels)
+
         def build(prefix, in_ch, stride, enc_depths, enc_ch, enc_head, enc_patch, dec_depths, dec_ch, dec_head,
                   dec_patch, T, nn_side):
             emb = Embedding(in_ch, enc_ch[0])
@@ -624,9 +658,12 @@ class PointTransformerV3(nn.Module):
             ops.rows_uniform_flag(t_emb, ops.offset2batch(offset.long().contiguous(), t_emb.shape[0]),
                                   offset.long().contiguous(), flags)
         plan = Plan(grid, offset, self.order, self.n_cfg["stride"], self.c_cfg["stride"] if self.condition else None,
-                    self.shuffle_orders, perm_fn, flags)
+                    self.shuffle_orders, perm_fn, flags, spec=self.plan_spec)
         self.last_plan = plan
         nl = plan.n_levels
+        native = self._forward_native(plan, c_point, n_point, t_emb, exact)
+        if native is not None:
+            return native
         n = self._prep(n_point, nl[0])
         n = self._n_embedding(n)
         if not self.condition:
@@ -664,7 +701,7 @@ class PointTransformerV3(nn.Module):
         side = self._side_stream(main) if self.overlap_streams else main
         two = side is not main
         if two:
-            nl[0].nbr(5); nl[0].nbr(3); nl[0].tile_mask(3); nl[0].conv_plan(3)          # level-0 tables are shared by both branches: build first
+            plan.arena.record_stream(side)                              # every table / slot map the side stream reads lives in the plan arena
             for k in ("feat", "coord", "t_scene", "t_emb"):
                 if k in c and torch.is_tensor(c[k]):
                     c[k].record_stream(side)
@@ -691,6 +728,46 @@ class PointTransformerV3(nn.Module):
         if two:
             main.wait_stream(side)
         return self._export(c), self._export(n)
+
+    def _forward_native(self, plan, c_point, n_point, t_emb, mode):
+        """the whole feature phase through cdseg_net_forward (csrc/net_exec.cu); None when this forward needs the per-module path
+        (per-point timestep rows that differ inside a scene, ops.NATIVE_NET off, comparator GEMM / attention kernels selected)"""
+        from . import netexec
+        if not netexec.supported(self) or (mode == "f16" and ops.ATTN_KERNEL != 3):
+            return None
+        ts = None
+        offset = n_point["offset"]
+        B = offset.numel()
+        if self.condition and t_emb is not None:
+            if self.t_emb_per_scene and t_emb.shape[0] == B and B != n_point["feat"].shape[0]:
+                ts = t_emb                                              # already one row per scene
+            elif self.t_emb_per_scene and plan.flags is not None and int(plan.flags[0]) == 0:
+                first = torch.cat([offset.new_zeros(1), offset[:-1]]).long()
+                ts = t_emb.index_select(0, first).contiguous()           # rows are identical inside a scene
+            else:
+                return None
+        for d in (n_point, c_point):
+            if d is not None and not (d["feat"].is_cuda and d["coord"].is_cuda):
+                raise RuntimeError("cdsegnet_b200: inputs must be CUDA tensors (no CPU fallback)")
+        main = torch.cuda.current_stream()
+        side = self._side_stream(main) if (self.overlap_streams and self.condition) else None
+        n_feat = n_point["feat"].float().contiguous()
+        c_feat = c_point["feat"].float().contiguous() if self.condition else None
+        n_out, c_out = netexec.forward_native(self, plan, n_feat, c_feat, ts, mode, main, side)
+
+        def export(d, feat, level):
+            p = Point(d)
+            p["feat"] = feat
+            p["coord"] = d["coord"].float()
+            p.pop("t_emb", None)
+            p["_level"] = level
+            p["serialized_depth"] = level.depth
+            p["_export_level"] = level
+            return p
+        n = export(n_point, n_out, plan.n_levels[0])
+        if not self.condition:
+            return n
+        return export(c_point, c_out, plan.c_levels[0]), n
 
     def _side_stream(self, main):
         key = main.device

@@ -4,83 +4,133 @@
 
 Design (see DESIGN.md "Plan phase"): everything that depends only on ``grid_coord`` /
 ``offset`` -- curve codes, the four sorted orders, the whole pooling hierarchy of BOTH
-networks, cluster ids, pooled codes/orders -- is computed up front by sync-free kernels
-(pooled counts stay in device memory), followed by ONE device->host copy of the level
-sizes.  Neighbour tables and patch slot maps are then built lazily per level and cached
-(the analogue of spconv's ``indice_key`` and of the reference's cached "pad"/"unpad").
+networks, cluster ids, pooled codes/orders, neighbour tables, tap masks, conv tile plans
+and patch slot maps -- is computed up front by ONE C-ABI call (``cdseg_plan_build``,
+csrc/plan_exec.cu) that enqueues the sync-free kernels from C++ and synchronises twice
+(depth + offsets; pooled level sizes).  The Python objects below are thin views over the
+descriptors that call fills in; tensors are materialised lazily, only for callers that
+read them (tests, exported ``Point`` fields, the launch-by-launch debug path).
 
 Row bookkeeping: arrays are stored in *physical* curve order (the order of the ``order``
 argument); the reference's ``shuffle_orders`` row permutations (CPU ``torch.randperm``,
 structure.py:95, ptv3.py:502) only permute ``rowmap`` (logical row -> physical row).
 """
+import ctypes
+
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
+from ._lib import check
+
+_DT = {torch.int32: 4, torch.int64: 8, torch.uint8: 1, torch.float32: 4}
 
 
 class Level:
-    """One resolution level of one network."""
+    """One resolution level of one network: a view over a CdsegPlanLevel descriptor."""
 
-    def __init__(self):
-        self.n = None            # number of points (host int, known after finalize())
-        self.cap = None          # allocated rows
-        self.B = None
-        self.grid = None         # int32 [cap,3]
-        self.batch = None        # int32 [cap]
-        self.offset_host = None  # np.int64 [B] cumulative
-        self.offset_dev = None   # int64 [B]
-        self.code = None         # int64 [k, cap]  physical rows
-        self.order = None        # int32 [k, cap]
-        self.inverse = None      # int32 [k, cap]
-        self.depth = None
-        self.rowmap = None       # list: logical row -> physical row
+    def __init__(self, plan, index, k):
+        self._plan, self._i, self._k = plan, index, k
+        self.d = plan.desc[index]
         self.parent = None
-        self.cluster = None      # int32 [parent.cap]   parent point -> this level's point (pooling_inverse)
-        self.idx_ptr = None      # int32 [cap+1]
-        self.head = None         # int32 [cap]
-        self.c0 = None           # physical row of the parent that defined the clusters
-        self.pooling_depth = None
-        self.m_dev = None
-        self.perm = None         # level 0 only: internal id r <-> original point perm[r] (see Plan)
-        self.inv_perm = None
-        self.orig = None         # level 0 only: (code, order, inverse) in the caller's numbering
+        self._cache = {}
         self._nbr = {}
         self._pm = {}
         self._pad_K = None       # patch size the reference would have cached its pad maps with
 
-    # ---- lazily built, cached structures --------------------------------------------
+    # ---- host scalars --------------------------------------------------------------------
+    n = property(lambda s: int(s.d.n))
+    cap = property(lambda s: int(s.d.cap))
+    B = property(lambda s: int(s.d.B))
+    depth = property(lambda s: int(s.d.depth))
+    c0 = property(lambda s: int(s.d.c0))
+    pooling_depth = property(lambda s: int(s.d.pooling_depth))
+    rowmap = property(lambda s: [int(s.d.rowmap[i]) for i in range(s._k)])
+
+    @property
+    def offset_host(self):
+        return np.array([self.d.offset_host[b] for b in range(self.d.B)], dtype=np.int64)
+
+    # ---- device arrays (lazy views into the plan arena) ------------------------------------
+    def _view(self, key, ptr, shape, dtype):
+        t = self._cache.get(key)
+        if t is None:
+            t = self._plan.view(ptr, shape, dtype) if ptr else None
+            self._cache[key] = t
+        return t
+
+    grid = property(lambda s: s._view("grid", s.d.grid, (s.cap, 3), torch.int32))
+    batch = property(lambda s: s._view("batch", s.d.batch, (s.cap,), torch.int32))
+    code = property(lambda s: s._view("code", s.d.code, (s._k, s.cap), torch.int64))
+    order = property(lambda s: s._view("order", s.d.order, (s._k, s.cap), torch.int32))
+    inverse = property(lambda s: s._view("inverse", s.d.inverse, (s._k, s.cap), torch.int32))
+    cluster = property(lambda s: s._view("cluster", s.d.cluster, (s.cap,), torch.int32))
+    idx_ptr = property(lambda s: s._view("idx_ptr", s.d.idx_ptr, (s.cap + 1,), torch.int32))
+    head = property(lambda s: s._view("head", s.d.head, (s.cap,), torch.int32))
+    perm = property(lambda s: s._view("perm", s.d.perm, (s.cap,), torch.int32))
+    inv_perm = property(lambda s: s._view("inv_perm", s.d.inv_perm, (s.cap,), torch.int32))
+
+    @property
+    def orig(self):
+        """level 0 only: (code, order, inverse) in the caller's numbering"""
+        if not self.d.o_code:
+            return None
+        return (self._view("o_code", self.d.o_code, (self._k, self.cap), torch.int64),
+                self._view("o_order", self.d.o_order, (self._k, self.cap), torch.int32),
+                self._view("o_inverse", self.d.o_inverse, (self._k, self.cap), torch.int32))
+
+    # ---- indice tables / slot maps: prebuilt by the plan call when the model asked for them, else built on demand ----------
     def scene_count(self):
         return np.diff(self.offset_host, prepend=0)
 
     def nbr(self, ksize):
         if ksize not in self._nbr:
-            self._nbr[ksize] = ops.nbr_build(self.grid[: self.n], self.batch[: self.n], ksize)
+            if ksize == 3 and self.d.nbr3:
+                self._nbr[3] = self._plan.view(self.d.nbr3, (self.n, 27), torch.int32)
+            elif self.d.nbr_stem and ksize == self.d.stem_ksize:
+                self._nbr[ksize] = self._plan.view(self.d.nbr_stem, (self.n, ksize ** 3), torch.int32)
+            else:
+                self._nbr[ksize] = ops.nbr_build(self.grid[: self.n], self.batch[: self.n], ksize)
         return self._nbr[ksize]
 
     def tile_mask(self, ksize):
         """per 128-row tile bitmask of the taps that occur (lets the conv GEMM skip absent taps)"""
         key = ("mask", ksize)
         if key not in self._nbr:
-            self._nbr[key] = ops.tile_tap_mask(self.nbr(ksize))
+            if ksize == 3 and self.d.tile_mask3:
+                self._nbr[key] = self._plan.view(self.d.tile_mask3, ((self.n + 127) // 128,), torch.int32)
+            else:
+                self._nbr[key] = ops.tile_tap_mask(self.nbr(ksize))
         return self._nbr[key]
 
     def conv_plan(self, ksize):
         """per 128-row tile: distinct neighbour rows + local indices (operand cache plan of the fused pre-attention kernel)"""
         key = ("plan", ksize)
         if key not in self._nbr:
-            self._nbr[key] = ops.conv_tile_plan(self.nbr(ksize))
+            if ksize == 3 and self.d.conv_plan3:
+                nb = int(_lib.load().cdseg_conv_plan_bytes(self.n))
+                self._nbr[key] = self._plan.view(self.d.conv_plan3, (nb,), torch.uint8)
+            else:
+                self._nbr[key] = ops.conv_tile_plan(self.nbr(ksize))
         return self._nbr[key]
 
     def patch_maps(self, order_index, K):
         """slot maps of logical curve `order_index`.  Like the reference (ptv3.py:191-244 caches
         "pad"/"unpad" on the Point), the FIRST patch size used at a level sticks."""
         if self._pad_K is None:
-            self._pad_K = K
+            self._pad_K = int(self.d.K) if self.d.K > 0 else K
         K = self._pad_K
         prow = self.rowmap[order_index]
         if prow not in self._pm:
-            self._pm[prow] = ops.patch_maps(self.order[prow][: self.n], self.scene_count(), K)
+            m = self.d.pm[order_index]
+            if m.T > 0 and m.K == K and (self.d.pm_mask >> order_index) & 1:
+                T, Kp = int(m.T), int(m.Kp)
+                v = self._plan.view
+                self._pm[prow] = dict(slot_src=v(m.slot_src, (T * Kp,), torch.int32), slot_dst=v(m.slot_dst, (T * Kp,), torch.int32),
+                                      point_slot=v(m.point_slot, (self.n,), torch.int32), patch_len=v(m.patch_len, (T,), torch.int32),
+                                      T=T, Kp=Kp, K=K, pairs=int(m.pairs))
+            else:
+                self._pm[prow] = ops.patch_maps(self.order[prow][: self.n], self.scene_count(), K)
         return self._pm[prow]
 
     def members(self):
@@ -131,102 +181,90 @@ def torch_randperm(k):
 class Plan:
     """Serialization + pooling hierarchy of the CN (code prefix n_) and, if `c_strides`
     is given, the NN (code prefix c_).  Mirrors the reference's RNG call order so that a
-    seeded run reproduces the reference's shuffles."""
+    seeded run reproduces the reference's shuffles.
+
+    `spec` (optional, from the model): dict(n=[...], c=[...]) with one dict(K=patch size, mask=logical curves whose slot maps are
+    needed, conv_plan=bool, stem=kernel size or 0) per level; the tables are then built inside the same native call.  Without it
+    (direct users, tests) they are built on first use."""
 
     def __init__(self, grid_coord, offset, orders, n_strides, c_strides=None, shuffle_orders=True, perm_fn=None,
-                 extra_flags=None):
+                 extra_flags=None, spec=None):
         perm_fn = perm_fn or torch_randperm
         dev = grid_coord.device
+        if dev.type != "cuda":
+            raise _lib.CdsegError("cdsegnet_b200 kernels need CUDA tensors (there is no CPU fallback)")
         k = len(orders)
         grid = grid_coord.to(torch.int32).contiguous()
         N = grid.shape[0]
         B = offset.numel()
         offset = offset.to(torch.int64).contiguous()
-        # --- sync #1: depth + offsets (the reference syncs here too: structure.py:66) ---------
-        gm = ops.grid_max(grid)
-        head = torch.cat([gm.to(torch.int64), offset]).cpu().numpy()
-        depth = int(head[0]).bit_length()
-        if depth > 16:
-            raise ValueError("serialized depth > 16 (structure.py:74)")
-        offset_host = head[1:].astype(np.int64)
-        if int(offset_host[-1]) != N:
-            raise ValueError("offset[-1] != number of points")
-        nbits = 3 * depth + max(0, int(B - 1).bit_length())
-        batch = ops.offset2batch(offset, N)
-        code = ops.encode_codes(grid, batch, depth, orders)
-        order, inverse = ops.argsort_rows(code, nbits)
-        # Internal numbering = rank along the first curve: point r of the working set is the caller's
-        # point perm[r].  Every level-0 kernel (conv tiles, patch gathers, LayerNorm rows) then walks
-        # memory in space-filling-curve order; inputs are gathered once and the logits scattered back.
-        perm, inv_perm = order[0], inverse[0]
-        i_grid, i_batch, i_code, i_order, i_inverse = ops.renumber(perm, inv_perm, grid, batch, code, order, inverse)
-
-        def level0():
-            L = Level()
-            L.n = L.cap = N; L.B = B; L.grid = i_grid; L.batch = i_batch
-            L.offset_host = offset_host; L.offset_dev = offset
-            L.code, L.order, L.inverse, L.depth = i_code, i_order, i_inverse, depth
-            L.perm, L.inv_perm, L.orig = perm, inv_perm, (code, order, inverse)
-            return L
-
-        # RNG order of the reference forward (ptv3.py:1761-1794): c.serialization, n.serialization,
-        # then the poolings in module execution order.
-        self.c_levels = None
+        self._keep = (grid, offset)
+        n_n, n_c = len(n_strides) + 1, (len(c_strides) + 1 if c_strides is not None else 0)
+        n_lv = n_n + n_c
+        self.desc = (_lib.PlanLevel * n_lv)()
+        d = self.desc
+        # RNG order of the reference forward (ptv3.py:1761-1794): c.serialization, n.serialization, then the poolings in module
+        # execution order (c1, n1, n2, c2, n3, n4 for the shipped 3 / 5 stage schedule).
+        ident = list(range(k))
         if c_strides is not None:
-            c0 = level0()
-            c0.rowmap = _draw(k, perm_fn) if shuffle_orders else list(range(k))
-            self.c_levels = [c0]
-        n0 = level0()
+            rm_c0 = _draw(k, perm_fn) if shuffle_orders else ident
+        rm_n0 = _draw(k, perm_fn) if shuffle_orders else ident
+        rm = {("n", 0): rm_n0}
         if c_strides is not None:
-            n0._nbr = c0._nbr          # same points, same numbering: share the neighbour tables / tap masks
-
-        n0.rowmap = _draw(k, perm_fn) if shuffle_orders else list(range(k))
-        self.n_levels = [n0]
-
-        n_pool = len(n_strides) + (len(c_strides) if c_strides is not None else 0)
-        n_flag = extra_flags.numel() if extra_flags is not None else 0
-        # every pooled level's point count (int32) and per-scene offsets (int64) land in two small buffers: one zero fill and
-        # one device-to-host copy each per forward instead of a fill / cast / cat per level
-        cnt_buf = torch.zeros(max(n_pool, 1), dtype=torch.int32, device=dev)
-        off_buf = torch.zeros((max(n_pool, 1), B), dtype=torch.int64, device=dev)
-        slot = [0]
-
-        def pool(levels, stride):
-            par = levels[-1]
-            pd = (int(np.ceil(stride)) - 1).bit_length()
-            if pd > par.depth:
-                pd = 0
-            ch = Level()
-            ch.parent, ch.c0, ch.pooling_depth = par, par.rowmap[0], pd
-            ch.cap, ch.B, ch.depth = par.cap, B, par.depth - pd
-            i = slot[0]
-            slot[0] += 1
-            out = ops.pool_plan(par.code, par.order, par.m_dev, par.n if par.m_dev is None else 0, ch.c0, pd, par.grid,
-                                par.batch, B, ch.cap, cnt_buf[i:i + 1], off_buf[i])
-            ch.slot = i
-            ch.cluster, ch.idx_ptr, ch.head = out["cluster"], out["idx_ptr"], out["head"]
-            ch.code, ch.order, ch.inverse = out["code"], out["order"], out["inverse"]
-            ch.grid, ch.batch, ch.m_dev, ch.offset_dev = out["grid"], out["batch"], out["m_dev"], out["offset"]
-            perm = _draw(k, perm_fn)                    # SerializedPooling always shuffles (ptv3.py:501-505)
-            ch.rowmap = [par.rowmap[p] for p in perm]
-            levels.append(ch)
-
-        if c_strides is not None:
-            assert len(c_strides) == 2 and len(n_strides) == 4, "reference schedule is 3 NN / 5 CN stages"
-            pool(self.c_levels, c_strides[0]); pool(self.n_levels, n_strides[0]); pool(self.n_levels, n_strides[1])
-            pool(self.c_levels, c_strides[1]); pool(self.n_levels, n_strides[2]); pool(self.n_levels, n_strides[3])
+            rm[("c", 0)] = rm_c0
+            if len(c_strides) == 2 and len(n_strides) == 4:
+                sched = [("c", 1), ("n", 1), ("n", 2), ("c", 2), ("n", 3), ("n", 4)]
+            else:
+                raise NotImplementedError("the reference interleaves a 3-stage Noise Network with a 5-stage Conditional Network "
+                                          "(ptv3.py:1785-1794); other depth pairs have no defined shuffle order")
         else:
-            for s in n_strides:
-                pool(self.n_levels, s)
+            sched = [("n", s) for s in range(1, n_n)]
+        for net, s in sched:
+            perm = _draw(k, perm_fn)                    # SerializedPooling always shuffles (ptv3.py:501-505)
+            rm[(net, s)] = [rm[(net, s - 1)][p] for p in perm]
+        index = {("n", s): s for s in range(n_n)}
+        index.update({("c", s): n_n + s for s in range(n_c)})
+        K_all = []
+        for (net, s), i in index.items():
+            L = d[i]
+            L.parent = -1 if s == 0 else index[(net, s - 1)]
+            strides = n_strides if net == "n" else c_strides
+            L.stride = int(np.ceil(strides[s - 1])) if s > 0 else 0
+            for r in range(k):
+                L.rowmap[r] = rm[(net, s)][r]
+            sp = spec[net][s] if spec is not None else None
+            if sp is not None:
+                L.K, L.pm_mask, L.want_conv_plan, L.stem_ksize = int(sp["K"]), int(sp["mask"]), int(bool(sp["conv_plan"])), int(sp.get("stem", 0))
+                K_all.append(int(sp["K"]))
+        lib = _lib.load()
+        stem = max([int(d[i].stem_ksize) for i in range(n_lv)] + [0])
+        need = lib.cdseg_plan_arena_bytes(N, B, k, n_lv - (2 if n_c else 1), 2 if n_c else 1, stem, min(K_all) if K_all else 1024,
+                                          max(K_all) if K_all else 1024)
+        # one block from torch's caching allocator (an upper bound: the pooled sizes are only known inside the call); exported
+        # Points keep lazy views into it, so it is NOT shared between plans
+        self.arena = torch.empty(int(need), dtype=torch.uint8, device=dev)
+        self._base = self.arena.data_ptr()
+        ids = (ctypes.c_int * k)(*[ops.ORDER_IDS[o] for o in orders])
+        n_flags = extra_flags.numel() if extra_flags is not None else 0
+        fh = (ctypes.c_int32 * max(n_flags, 1))()
+        check(lib.cdseg_plan_build(grid.data_ptr(), offset.data_ptr(), N, B, ids, k, d, n_lv,
+                                   extra_flags.data_ptr() if n_flags else None, n_flags, fh, self._base, self.arena.numel(),
+                                   ops._stream()), "plan_build")
+        self.flags = np.array([fh[i] for i in range(n_flags)], dtype=np.int64) if n_flags else None
+        self.n_levels = [Level(self, index[("n", s)], k) for s in range(n_n)]
+        self.c_levels = [Level(self, index[("c", s)], k) for s in range(n_c)] if n_c else None
+        for levels in (self.n_levels, self.c_levels or []):
+            for s in range(1, len(levels)):
+                levels[s].parent = levels[s - 1]
+        if self.c_levels:
+            self.n_levels[0]._nbr = self.c_levels[0]._nbr          # same points, same numbering: share lazily built tables too
 
-        # --- sync #2: pooled sizes + offsets (+ caller flags) ------------------------------
-        pooled = [L for L in (self.c_levels or [])[1:] + self.n_levels[1:]]
-        self.flags = None
-        if pooled or extra_flags is not None:
-            cnt_host = cnt_buf.cpu().numpy()
-            off_host = off_buf.cpu().numpy()
-            for L in pooled:
-                L.n = int(cnt_host[L.slot])
-                L.offset_host = off_host[L.slot].astype(np.int64)
-            if extra_flags is not None:
-                self.flags = extra_flags.cpu().numpy().astype(np.int64).reshape(-1)
+    def view(self, ptr, shape, dtype):
+        """tensor view of arena memory (or of the caller's offset tensor) at raw device pointer `ptr`"""
+        nbytes = int(np.prod(shape)) * _DT[dtype]
+        off = ptr - self._base
+        if off < 0 or off + nbytes > self.arena.numel():
+            if ptr == self._keep[1].data_ptr():
+                return self._keep[1]
+            raise _lib.CdsegError("plan pointer outside the arena")
+        return self.arena[off: off + nbytes].view(dtype).view(shape)

@@ -47,6 +47,8 @@ int cdseg_argsort_rows(const int64_t* codes, int k, int64_t N, int nbits, int32_
  * slot_src/slot_dst: int32[T*Kp], point_slot: int32[N], patch_len: int32[T]  (T from cdseg_patch_count) */
 /* dst[i, :] = src[idx[i], :] for rows of row_bytes bytes (multiple of 4): feat[perm], coord[perm], logits[inv_perm] around the network */
 int cdseg_gather_rows(const void* src, const int32_t* idx, int64_t n, int row_bytes, void* dst, void* stream);
+/* dst[i, 0..C) = src[idx[i], 0..C), dst[i, C..Cp) = 0 (fp32 rows; the stem's zero-padded input in internal numbering) */
+int cdseg_gather_rows_pad(const float* src, const int32_t* idx, int64_t n, int C, int Cp, float* dst, void* stream);
 /* level-0 renumbering along the first curve (internal point r = original point perm[r], perm = order[0], inv_perm = inverse[0]):
  * grid / batch / code / inverse gathered by perm, order composed with inv_perm; code int64 [k,N], order / inverse int32 [k,N] */
 int cdseg_renumber(const int32_t* perm, const int32_t* inv_perm, const int32_t* grid, const int32_t* batch, const int64_t* code,
@@ -199,6 +201,36 @@ int cdseg_conv_tile_plan(const int32_t* nbr, int64_t n, void* plan, void* stream
  * the LayerNorms that follow it at the wide levels (default: all) */
 void cdseg_set_fused_mask(int mask);
 
+/* ---- native plan phase (plan_exec.cu): serialization + pooling hierarchy + indice tables + patch maps of BOTH networks in one call --
+ * Replaces Point.serialization (structure.py:47-102), the structural half of every SerializedPooling (ptv3.py:464-505), the spconv
+ * indice tables of Point.sparsify (structure.py:104-140) and get_padding_and_inverse (ptv3.py:188-244).  Two stream syncs inside
+ * (depth + offsets; pooled sizes).  Caller allocates the device arena; every pointer below points into it (or at the inputs). */
+#define CDSEG_MAX_SCENES 64
+typedef struct CdsegPatchMap {
+  int32_t* slot_src; int32_t* slot_dst; int32_t* point_slot; int32_t* patch_len;   /* [T*Kp], [T*Kp], [n], [T] */
+  int T, Kp, K, pad_; int64_t pairs;                                                /* pairs: algorithmic (query, key) pairs, padding excluded */
+} CdsegPatchMap;
+typedef struct CdsegPlanLevel {
+  /* in (host) */
+  int parent, stride;                 /* index of the level this one is pooled from (-1: a level-0 entry), pooling stride */
+  int rowmap[4];                      /* logical curve row -> physical row (the reference's shuffle_orders bookkeeping) */
+  int K; unsigned pm_mask;            /* patch size of this level's attention blocks; bit i: build the slot maps of logical curve i */
+  int want_conv_plan, stem_ksize;     /* fused pre-attention operand cache plan (C = 32 / 64 / 128 levels); stem conv kernel size (level 0, else 0) */
+  /* out (host) */
+  int64_t n, cap; int B, depth, c0, pooling_depth, slot, pad_;
+  int64_t offset_host[CDSEG_MAX_SCENES];
+  /* out (device) */
+  int32_t* grid; int32_t* batch; int64_t* code; int32_t* order; int32_t* inverse;      /* code / order / inverse: [k][cap], physical rows */
+  int32_t* cluster; int32_t* idx_ptr; int32_t* head; int32_t* m_dev; int64_t* offset_dev;  /* pooled levels: parent point -> this level, CSR, heads */
+  int32_t* perm; int32_t* inv_perm; int64_t* o_code; int32_t* o_order; int32_t* o_inverse; /* level 0: internal <-> caller numbering, originals */
+  int32_t* nbr3; uint32_t* tile_mask3; void* conv_plan3; int32_t* nbr_stem;
+  CdsegPatchMap pm[4];                /* by LOGICAL curve index */
+} CdsegPlanLevel;
+size_t cdseg_plan_arena_bytes(int64_t N, int B, int k, int n_levels, int n_level0, int stem_ksize, int K_min, int K_max);
+int cdseg_plan_build(const int32_t* grid, const int64_t* offset, int64_t N, int B, const int* order_ids, int k,
+                     CdsegPlanLevel* levels, int n_levels, const int32_t* extra_flags, int n_flags, int32_t* flags_host,
+                     void* arena, size_t arena_bytes, void* stream);
+
 /* ---- native executor of one PTv3 Block (ptv3.py:399-428): the 12-13 launches above enqueued from C++ in one call --- */
 #define CDSEG_ATTN_F16 0
 #define CDSEG_ATTN_EXACT 1
@@ -224,6 +256,53 @@ typedef struct CdsegBlockArgs {
 } CdsegBlockArgs;
 size_t cdseg_block_scratch_bytes(int64_t n, int C, int H, int T, int Kp, int B);
 int cdseg_block_forward(const CdsegBlockArgs* args, void* stream);
+/* ---- native executor of the whole feature phase (net_exec.cu): PointTransformerV3.forward, ptv3.py:1757-1845, after the plan ----
+ * Embedding stems, the interleaved encoder stages of both networks (Noise Network on a second stream), TransferModule, decoders,
+ * heads and the gathers between the caller's point numbering and the internal (curve-order) one: ~450 launches enqueued from ONE
+ * call instead of ~120 Python -> C transitions.  Weights are described once per model by CdsegNetW (packed operands from
+ * cdseg_gemm_pack_b, eval-mode BatchNorm folded into the packed weight / bias); levels come from cdseg_plan_build. */
+typedef struct CdsegLinW { const float* Bp; const float* bias; int K, N; } CdsegLinW;        /* y = x W^T + b (bias may be NULL) */
+typedef struct CdsegLnW { const float* g; const float* b; } CdsegLnW;
+typedef struct CdsegBlockW {                       /* Block, ptv3.py:325-428 */
+  int C, H, T_dim, order_index; float scale, ln_eps;
+  const float* conv_Bp; const float* conv_b; CdsegLinW lin; CdsegLnW cpe_ln; const float* t_W; const float* t_b;
+  CdsegLnW n1; CdsegLinW qkv, proj; CdsegLnW n2; CdsegLinW fc1, fc2;
+} CdsegBlockW;
+typedef struct CdsegPoolW { CdsegLinW proj; const float* bn_scale; const float* bn_shift; } CdsegPoolW;     /* SerializedPooling, ptv3.py:507-555 */
+typedef struct CdsegUnpoolW { CdsegLinW proj, proj_skip, cat_a, cat_b; int cat; float alpha; } CdsegUnpoolW;  /* SerializedUnpooling, ptv3.py:601-630 */
+typedef struct CdsegStageW { int n_blocks, has_pool, has_up, level; const CdsegBlockW* blocks; CdsegPoolW pool; CdsegUnpoolW up; } CdsegStageW;
+typedef struct CdsegStemW { const float* Bp; const float* shift; int cin, cout, ksize, pad_; } CdsegStemW;   /* Embedding, ptv3.py:633-663 */
+typedef struct CdsegCrossW {                       /* CrossBlock of the TransferModule, ptv3.py:1058-1223 (pre-norm, tm_feat a float) */
+  int Cq, Ckv, H, K; float scale, tm_feat, ln_eps; int pad_;
+  const float* q_conv_Bp; const float* q_conv_b; CdsegLinW q_lin; CdsegLnW q_cpe_ln;
+  const float* kv_conv_Bp; const float* kv_conv_b; CdsegLinW kv_lin; CdsegLnW kv_cpe_ln;
+  CdsegLnW q_norm1, kv_norm1, q_norm2; CdsegLinW q, kv, proj, fc1, fc2;
+} CdsegCrossW;
+#define CDSEG_MAX_STAGES 8
+typedef struct CdsegNetW {
+  int condition, T_dim, n_enc, n_dec, c_enc, c_dec, pad0_, pad1_;
+  CdsegStemW n_stem, c_stem;
+  CdsegStageW n_enc_st[CDSEG_MAX_STAGES], n_dec_st[CDSEG_MAX_STAGES], c_enc_st[CDSEG_MAX_STAGES], c_dec_st[CDSEG_MAX_STAGES]; /* dec: execution order */
+  CdsegLinW n_head, c_head;
+  const float* fc_t1_W; const float* fc_t1_b; const float* fc_t2_W; const float* fc_t2_b;
+  CdsegCrossW tm;
+} CdsegNetW;
+typedef struct CdsegForwardArgs {
+  const CdsegNetW* w; const CdsegPlanLevel* levels; int n_lv_n, n_lv_c;   /* levels[0 .. n_lv_n): CN, then n_lv_c NN levels */
+  int64_t N; int B, attn_mode;
+  const float* n_feat; const float* c_feat;       /* fp32 [N, cin], caller numbering */
+  const float* t_emb;                             /* fp32 [B, T_dim]: one timestep-embedding row per scene (NULL: no timestep branch) */
+  float* n_out; float* c_out;                     /* fp32 [N, n_head.N] / [N, c_head.N], caller numbering */
+  void* arena_main; size_t arena_main_bytes; void* arena_side; size_t arena_side_bytes;   /* >= cdseg_net_arena_bytes */
+  void* stream_main; void* stream_side;           /* stream_side NULL or == stream_main: everything on one stream */
+  void** block_events;                            /* optional: 6 cudaEvent_t per Block in execution order (CN blocks, then NN blocks), see CdsegBlockArgs.ev */
+} CdsegForwardArgs;
+int cdseg_net_arena_bytes(const CdsegForwardArgs* args, size_t* main_bytes, size_t* side_bytes);
+int cdseg_net_forward(const CdsegForwardArgs* args);
+/* sizeof(CdsegBlockArgs, CdsegPatchMap, CdsegPlanLevel, CdsegLinW, CdsegLnW, CdsegBlockW, CdsegPoolW, CdsegUnpoolW, CdsegStageW, CdsegStemW,
+ * CdsegCrossW, CdsegNetW, CdsegForwardArgs) in that order; returns how many there are.  For bindings to check their struct mirrors. */
+int cdseg_struct_sizes(size_t* out, int n);
+
 /* CUDA events for live per-kernel timing inside the timed region (bench.py) */
 void* cdseg_event_create(void);
 void cdseg_event_destroy(void* e);

@@ -147,3 +147,16 @@ def test_product_fails_loudly_without_cuda():
     m = cb.PointTransformerV3(**cfg).eval()
     with pytest.raises(Exception):
         m(n_point=dict(coord=t(z["coord"]), grid_coord=t(z["grid_coord"]), offset=t(z["offset"]), feat=t(z["feat"])))
+
+
+def test_ctypes_struct_mirrors_match_the_c_layouts(lib):
+    """every struct of the C ABI mirrored in Python (ctypes) has the size the compiler gave it"""
+    import ctypes
+    from cdsegnet_b200 import _lib, netexec
+    out = (ctypes.c_size_t * 16)()
+    n = lib.cdseg_struct_sizes(out, 16)
+    mirrors = [_lib.BlockArgs, _lib.PatchMap, _lib.PlanLevel, netexec.LinW, netexec.LnW, netexec.BlockW, netexec.PoolW, netexec.UnpoolW,
+               netexec.StageW, netexec.StemW, netexec.CrossW, netexec.NetW, netexec.ForwardArgs]
+    assert n == len(mirrors)
+    for i, m in enumerate(mirrors):
+        assert ctypes.sizeof(m) == out[i], (m.__name__, ctypes.sizeof(m), out[i])

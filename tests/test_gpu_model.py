@@ -206,3 +206,45 @@ def test_batch8_ragged_scenes_match_oracle():
     m, cfg, noise, perms, c_ref, n_ref = _oracle_case(scene, dict(enable_flash=False), cap=32)
     c, n = _run(m, cfg, scene, noise, perms)
     assert np.abs(n - n_ref).max() < 1e-3 and np.abs(c - c_ref).max() < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["tc32", "f16"])
+@pytest.mark.parametrize("name", ["case1_single", "case2_batch2", "case3_cn_only"])
+def test_native_net_executor_equals_per_module_path(name, mode):
+    """cdseg_net_forward (one C-ABI call for the whole feature phase) launches the same kernels as the module-by-module Python path:
+    identical logits, with either stream schedule"""
+    from cdsegnet_b200 import ops
+    z, cfg, shapes = load_case(name)
+    outs = {}
+    for native in (True, False):
+        ops.NATIVE_NET = native
+        try:
+            c, n, m = run_cuda(z, cfg, shapes, exact=True, mode=mode)
+        finally:
+            ops.NATIVE_NET = True
+        outs[native] = (n["feat"].cpu().numpy(), None if c is None else c["feat"].cpu().numpy())
+    assert np.array_equal(outs[True][0], outs[False][0])
+    if outs[True][1] is not None:
+        assert np.array_equal(outs[True][1], outs[False][1])
+
+
+def test_native_net_single_stream_and_repeat():
+    """native executor with overlap_streams off, and repeated forwards on recycled arenas"""
+    z, cfg, shapes = load_case("case2_batch2")
+    import cdsegnet_b200 as cb
+    from cdsegnet_b200.segmentor import calc_t_emb
+    for overlap in (False, True):
+        m = cb.PointTransformerV3(**dict(cfg, enable_flash=False))
+        m.load_state_dict(synth_state_dict(shapes), strict=True)
+        m = m.to(DEV).eval()
+        m.overlap_streams = overlap
+        base = dict(coord=t(z["coord"]).to(DEV), grid_coord=t(z["grid_coord"]).to(DEV), offset=t(z["offset"]).to(DEV))
+        ts = 999 * torch.ones((len(z["coord"]), 1), dtype=torch.int64, device=DEV)
+        for _ in range(3):
+            c, n = m(dict(base, feat=t(z["noise"]).to(DEV), t_emb=calc_t_emb(ts, 128)), dict(base, feat=t(z["feat"]).to(DEV)),
+                     perm_fn=replay(z["perms"]))
+            torch.cuda.synchronize()
+            assert np.abs(n["feat"].cpu().numpy() - z["n_feat"]).max() < 1e-3
+            assert np.abs(c["feat"].cpu().numpy() - z["c_feat"]).max() < 1e-3
+            for key in ("serialized_code", "serialized_order", "serialized_inverse"):
+                assert np.array_equal(n[key].cpu().numpy(), z[key]), key
