@@ -134,6 +134,8 @@ SIGNATURES = {
     "cdseg_scale_shift_act": (_I, [_P, _P, _P, _I, _L, _I, _P, _P]),
     "cdseg_small_linear": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "cdseg_rows_uniform": (_I, [_P, _P, _P, _L, _I, _P, _P]),
+    "cdseg_set_gemm_precision": (None, [_I]),
+    "cdseg_get_gemm_precision": (_I, []),
     "cdseg_gemm_packed_b_floats": (_Z, [_I, _I, _I]),
     "cdseg_gemm_pack_b": (_I, [_P, _I, _I, _I, _P, _P]),
     "cdseg_tile_tap_mask": (_I, [_P, _L, _I, _P, _P]),
@@ -149,6 +151,7 @@ SIGNATURES = {
     "cdseg_plan_build": (_I, [_P, _P, _L, _I, ctypes.POINTER(_I), _I, ctypes.POINTER(PlanLevel), _I, _P, _I, ctypes.POINTER(ctypes.c_int32), _P, _Z, _P]),
     "cdseg_net_arena_bytes": (_I, [_P, ctypes.POINTER(_Z), ctypes.POINTER(_Z)]),
     "cdseg_net_forward": (_I, [_P]),
+    "cdseg_net_set_debug": (None, [_I]),
     "cdseg_struct_sizes": (_I, [ctypes.POINTER(_Z), _I]),
     "cdseg_gather_rows_pad": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "cdseg_set_fused_mask": (None, [_I]),

@@ -30,6 +30,7 @@ struct PostParams {
   float eps;
   const __half *Bp_proj, *Bp_fc1, *Bp_fc2;
   const float *b_proj, *ln_g, *ln_b, *b_fc1, *b_fc2;
+  int single;                                   // fp16 x fp16 products only (cdseg_set_gemm_precision)
 };
 
 struct PostBars {
@@ -212,9 +213,13 @@ post_kernel(const PostParams p, const __grid_constant__ CUtensorMap tmO, const _
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           const uint64_t dh = make_desc(bh + ks * 256, 128, 512), dl = make_desc(bl + ks * 256, 128, 512);
-          umma_f16_ts(d, a + 16 + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
-          umma_f16_ts(d, a + ks * 8, dl, idesc, 1u);
-          umma_f16_ts(d, a + ks * 8, dh, idesc, 1u);
+          if (p.single) {
+            umma_f16_ts(d, a + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
+          } else {
+            umma_f16_ts(d, a + 16 + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
+            umma_f16_ts(d, a + ks * 8, dl, idesc, 1u);
+            umma_f16_ts(d, a + ks * 8, dh, idesc, 1u);
+          }
         }
         umma_commit(smem_u32(&bars->b_empty[s]));
         ++b_it;
@@ -267,6 +272,8 @@ int cdseg_make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64
   return r == CUDA_SUCCESS ? CDSEG_OK : CDSEG_EINVAL;
 }
 
+extern int g_cdseg_gemm_single;                  // gemm_tc.cu
+
 static int sm_count() {
   static int n = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
   return n;
@@ -287,6 +294,7 @@ CDSEG_API int cdseg_post_attn(const float* o, const float* x1, int64_t n, int C,
   fz::PostParams p;
   p.M = (int)n; p.C = C; p.ntiles = cdseg_div_up(n, fz::BM); p.eps = eps;
   p.tmem_cols = C <= 64 ? 256 : 512;
+  p.single = g_cdseg_gemm_single;
   p.Bp_proj = reinterpret_cast<const __half*>(proj_Bp); p.Bp_fc1 = reinterpret_cast<const __half*>(fc1_Bp);
   p.Bp_fc2 = reinterpret_cast<const __half*>(fc2_Bp);
   p.b_proj = proj_b; p.ln_g = ln_g; p.ln_b = ln_b; p.b_fc1 = fc1_b; p.b_fc2 = fc2_b;

@@ -46,6 +46,7 @@ struct PreParams {
   const float *b_conv, *b_lin, *cpe_g, *cpe_b, *n1_g, *n1_b, *b_qkv;
   const float* tproj; const int32_t* batch;     // [B, C] per-scene timestep projection + scene id per row, or NULL
   long long* trace; int trace_cta;              // profiling hook (cdseg_pre_attn_set_trace): clock64 stamps of one CTA, null in production
+  int single;                                   // fp16 x fp16 products only (cdseg_set_gemm_precision)
 };
 
 struct PreBars {
@@ -389,9 +390,13 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           const uint64_t dh = make_desc(bh + ks * 256, 128, 512), dl = make_desc(bl + ks * 256, 128, 512);
-          umma_f16_ts(d, a + 16 + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
-          umma_f16_ts(d, a + ks * 8, dl, idesc, 1u);
-          umma_f16_ts(d, a + ks * 8, dh, idesc, 1u);
+          if (p.single) {
+            umma_f16_ts(d, a + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
+          } else {
+            umma_f16_ts(d, a + 16 + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
+            umma_f16_ts(d, a + ks * 8, dl, idesc, 1u);
+            umma_f16_ts(d, a + ks * 8, dh, idesc, 1u);
+          }
         }
         umma_commit(smem_u32(&bars->b_empty[s]));
         ++b_it;
@@ -491,6 +496,7 @@ __global__ void __launch_bounds__(BM) conv_tile_plan_kernel(const int32_t* __res
 
 static long long* g_pre_trace = nullptr;
 static int g_pre_trace_cta = 0;
+extern int g_cdseg_gemm_single;                  // gemm_tc.cu
 CDSEG_API void cdseg_pre_attn_set_trace(long long* buf, int cta) { g_pre_trace = buf; g_pre_trace_cta = cta; }
 
 static int sm_count_pre() {
@@ -532,6 +538,7 @@ CDSEG_API int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, in
   p.b_conv = conv_b; p.b_lin = lin_b; p.cpe_g = cpe_g; p.cpe_b = cpe_b; p.n1_g = n1_g; p.n1_b = n1_b; p.b_qkv = qkv_b;
   p.tproj = tproj; p.batch = batch;
   p.trace = g_pre_trace; p.trace_cta = g_pre_trace_cta;
+  p.single = g_cdseg_gemm_single;
   const int per_sm = C <= 64 ? 2 : 1;
   size_t smem = (size_t)fz::Q_CACHE + (size_t)fz::Q_SB * fz::B_STAGE + fz::Q_LIDX + fz::Q_PAR * 4 + sizeof(fz::PreBars) + 1024;
   if (per_sm == 1) smem = smem > 120 * 1024 ? smem : 120 * 1024;

@@ -106,6 +106,7 @@ struct Params {
   int vec_ok;                             // output / residual rows are 16-byte aligned
   int AT, SB, b_bytes, acc_cols, tmem_cols;   // A ring slots (TMEM), B ring stages (smem), bytes of one B block, TMEM layout
   long long* trace; int trace_cta;        // profiling hook: clock64 stamps of one CTA (null in production)
+  int single;                             // 1: fp16 x fp16 products only (hi.hi; the lo terms are skipped): the reduced-precision mode
 };
 
 constexpr int MAX_RING = 4;
@@ -385,9 +386,13 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
 #pragma unroll
         for (int ks = 0; ks < KC / 16; ++ks) {                   // K = 16 per MMA: 8 TMEM columns of A, 2 core matrices (256 B) of B
           const uint64_t bh = make_desc(b_hi + ks * 256, 128, (KC / 8) * 128), bl = make_desc(b_lo + ks * 256, 128, (KC / 8) * 128);
-          umma_f16_ts(tmem, a_lo + ks * 8, bh, idesc, (it | ks) != 0);     // small terms first
-          umma_f16_ts(tmem, a_hi + ks * 8, bl, idesc, 1);
-          umma_f16_ts(tmem, a_hi + ks * 8, bh, idesc, 1);
+          if (p.single) {
+            umma_f16_ts(tmem, a_hi + ks * 8, bh, idesc, (it | ks) != 0);
+          } else {
+            umma_f16_ts(tmem, a_lo + ks * 8, bh, idesc, (it | ks) != 0);   // small terms first
+            umma_f16_ts(tmem, a_hi + ks * 8, bl, idesc, 1);
+            umma_f16_ts(tmem, a_hi + ks * 8, bh, idesc, 1);
+          }
         }
         umma_commit(smem_u32(&bars->empty_a[q]));                // each commit tracks every MMA issued so far
         umma_commit(smem_u32(&bars->empty_b[s]));
@@ -490,6 +495,12 @@ static bool g_narrow = [] { const char* e = getenv("CDSEG_GEMM_NARROW"); return 
 CDSEG_API void cdseg_gemm_tc_set_narrow(int on) { g_narrow = on != 0; }
 static long long* g_trace = nullptr;
 static int g_trace_cta = 0;
+// Dense-layer precision of the whole library (gemm_tc, fused pre / post kernels, stem): 0 = fp32-faithful (x = hi + lo fp16 halves,
+// three MMAs per product term), 1 = fp16 operands with fp32 accumulation (one MMA; the numerics of the reference's autocast training
+// and of BASELINE.json's reduced-precision configs).
+int g_cdseg_gemm_single = [] { const char* e = getenv("CDSEG_GEMM_FP16"); return e && atoi(e) != 0 ? 1 : 0; }();
+CDSEG_API void cdseg_set_gemm_precision(int fp16_single) { g_cdseg_gemm_single = fp16_single ? 1 : 0; }
+CDSEG_API int cdseg_get_gemm_precision(void) { return g_cdseg_gemm_single; }
 // profiling hook: clock64 stamps of CTA (cta,0,0) of subsequent launches into a device buffer of >= 16 int64; NULL disables
 CDSEG_API void cdseg_gemm_tc_set_trace(long long* buf, int cta) { g_trace = buf; g_trace_cta = cta; }
 
@@ -545,6 +556,7 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   p.part = (float*)workspace; p.nsplit = nsplit; p.nw = nw;
   p.AT = AT; p.SB = SB; p.b_bytes = b_bytes; p.acc_cols = acc_cols; p.tmem_cols = tmem_cols;
   p.trace = g_trace; p.trace_cta = g_trace_cta;
+  p.single = g_cdseg_gemm_single;
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + nw - 1) / nw, nsplit);

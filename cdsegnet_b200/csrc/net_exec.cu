@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "../../include/cdseg_b200.h"
 #include <cstring>
+#include <cstdlib>
+#include <cstdio>
 
 namespace {
 
@@ -23,10 +25,13 @@ int pick_split(int64_t tiles, int T) {
   return T;
 }
 
+int g_net_debug = [] { const char* e = getenv("CDSEG_NET_DEBUG"); return e ? atoi(e) : 0; }();
+
 struct Arena {
   char* base; size_t cap; size_t off; size_t high; bool dry;
   void* take(size_t bytes) {
     const size_t o = off;
+    if (!dry && (g_net_debug & 4)) fprintf(stderr, "[net] arena %p alloc off=%zu bytes=%zu\n", (void*)base, o, bytes);
     off += al256(bytes);
     if (off > high) high = off;
     return dry ? (void*)(uintptr_t)(0x1000 + o) : (void*)(base + o);     // dry: fake non-NULL addresses, never dereferenced
@@ -96,6 +101,8 @@ float* block(Ctx& c, const CdsegBlockW& w, const CdsegPlanLevel& L, const float*
   b.t_W = w.t_W; b.t_b = w.t_b; b.n1_g = w.n1.g; b.n1_b = w.n1.b; b.qkv_Bp = w.qkv.Bp; b.qkv_b = w.qkv.bias;
   b.proj_Bp = w.proj.Bp; b.proj_b = w.proj.bias; b.n2_g = w.n2.g; b.n2_b = w.n2.b; b.fc1_Bp = w.fc1.Bp; b.fc1_b = w.fc1.bias;
   b.fc2_Bp = w.fc2.Bp; b.fc2_b = w.fc2.bias; b.ln_eps = w.ln_eps; b.attn_mode = c.a->attn_mode;
+  if ((g_net_debug & 8) && c.st == (cudaStream_t)c.a->stream_side) b.attn_mode = CDSEG_ATTN_EXACT;       // debug: SIMT attention on the side stream
+  if ((g_net_debug & 16) && c.st == (cudaStream_t)c.a->stream_main) b.attn_mode = CDSEG_ATTN_EXACT;      // debug: SIMT attention on the main stream
   b.out = out; b.scratch = c.scratch; b.scratch_bytes = c.scratch_bytes;
   if (c.a->block_events)
     for (int i = 0; i < 6; ++i) b.ev[i] = c.a->block_events[(size_t)c.ev_index * 6 + i];
@@ -294,6 +301,7 @@ int walk(const CdsegForwardArgs* a, bool dry, Sizes* sz) {
     cx = stem(c, w.c_stem, lv[cb], a->c_feat);
     for (int s = 0; s < w.c_enc; ++s) { cx = enc_stage(c, w.c_enc_st[s], lv, cb, cx, t_scene); c_skip[s] = cx; }
     if (two && !dry) cudaEventRecord(g_ev[1], ss);
+    if (two && !dry && (g_net_debug & 1)) cudaStreamWaitEvent(sm, g_ev[1], 0);          // debug: serialise the two encoders
   }
   // ---- Conditional Network encoder (main stream) ----
   float* n_skip[CDSEG_MAX_STAGES] = {nullptr};
@@ -311,6 +319,7 @@ int walk(const CdsegForwardArgs* a, bool dry, Sizes* sz) {
     for (int j = 0; j < w.c_dec; ++j) cx = dec_stage(c, w.c_dec_st[j], lv, cb, cx, c_skip[w.c_dec_st[j].level], t_scene);
     head(c, w.c_head, lv[cb], cx, a->c_out);
     if (two && !dry) cudaEventRecord(g_ev[3], ss);
+    if (two && !dry && (g_net_debug & 2)) cudaStreamWaitEvent(sm, g_ev[3], 0);          // debug: serialise the two decoders
   }
   // ---- Conditional Network decoder + head (main stream) ----
   for (int j = 0; j < w.n_dec; ++j) nx = dec_stage(cm, w.n_dec_st[j], lv, nb, nx, n_skip[w.n_dec_st[j].level], nullptr);
@@ -339,6 +348,10 @@ void totals(const CdsegForwardArgs* a, const Sizes& z, size_t* m, size_t* s) {
 }
 
 }  // namespace
+
+// debug / profiling switches (also env CDSEG_NET_DEBUG): bit 0 serialise the two encoders, bit 1 serialise the two decoders,
+// bit 2 log every arena allocation to stderr
+CDSEG_API void cdseg_net_set_debug(int flags) { g_net_debug = flags; }
 
 CDSEG_API int cdseg_net_arena_bytes(const CdsegForwardArgs* args, size_t* main_bytes, size_t* side_bytes) {
   Sizes z{};

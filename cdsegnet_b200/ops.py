@@ -368,6 +368,14 @@ def pre_attn(conv_in, x, nbr, tile_mask, plan, conv, lin, cpe_ln, n1_ln, qkv, tp
     return x1, out
 
 
+def set_gemm_precision(kind):
+    """"fp32": every dense layer / conv on the 3-term fp16 hi/lo split (fp32-class results, default); "fp16": fp16 operands with fp32
+    accumulation, one MMA per product term -- the numerics of the reference's autocast training (engines/train.py:226)"""
+    if kind not in ("fp32", "fp16"):
+        raise ValueError(kind)
+    _lib.load().cdseg_set_gemm_precision(int(kind == "fp16"))
+
+
 def set_fused_mask(mask):
     _lib.load().cdseg_set_fused_mask(int(mask))
 

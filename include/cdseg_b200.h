@@ -150,6 +150,10 @@ int cdseg_rows_uniform(const float* x, const int32_t* batch, const int64_t* offs
  *      the path (ptv3.py:185-186, 311-313, 359, 458, 575-581, 911-913) ------------------------------------------ */
 /* W fp32 [T][K][N] (tap-major transposed conv weight, or weight^T of a Linear with T=1; K % 16 == 0)
  * -> Bp: cdseg_gemm_packed_b_floats(T,K,N) floats of pre-split (hi|lo), pre-tiled UMMA operand blocks */
+/* dense-layer precision of every tcgen05 GEMM in the library (gemm_tc, conv, fused pre / post kernels, stem): 0 (default) = fp32-faithful
+ * 3-term fp16 hi/lo split; 1 = fp16 operands, fp32 accumulation, one MMA per term (the reference's autocast numerics) */
+void cdseg_set_gemm_precision(int fp16_single);
+int cdseg_get_gemm_precision(void);
 size_t cdseg_gemm_packed_b_floats(int T, int K, int N);
 int cdseg_gemm_pack_b(const float* W, int T, int K, int N, float* Bp, void* stream);
 /* mask[tile] bit t = some row of the 128-row tile has neighbour t (nbr int32 [M,T], T <= 32) */
@@ -299,6 +303,8 @@ typedef struct CdsegForwardArgs {
 } CdsegForwardArgs;
 int cdseg_net_arena_bytes(const CdsegForwardArgs* args, size_t* main_bytes, size_t* side_bytes);
 int cdseg_net_forward(const CdsegForwardArgs* args);
+/* debug switches of the executor: bit 0 / 1 serialise the encoders / decoders of the two networks, bit 2 logs arena allocations */
+void cdseg_net_set_debug(int flags);
 /* sizeof(CdsegBlockArgs, CdsegPatchMap, CdsegPlanLevel, CdsegLinW, CdsegLnW, CdsegBlockW, CdsegPoolW, CdsegUnpoolW, CdsegStageW, CdsegStemW,
  * CdsegCrossW, CdsegNetW, CdsegForwardArgs) in that order; returns how many there are.  For bindings to check their struct mirrors. */
 int cdseg_struct_sizes(size_t* out, int n);

@@ -54,7 +54,7 @@ for _ in range(5):
 t_host = (time.perf_counter() - t0) / 5
 torch.cuda.synchronize()
 print(f"host per forward {1e3*t_host:.2f} ms: Plan.__init__ (incl. its 2 syncs) {1e3*accP['t']/5:.2f} ms, Block._native {1e3*acc['t']/5:.2f} ms over {acc['n']//5} calls "
-      f"({1e6*acc['t']/acc['n']:.1f} us per block call), everything else {1e3*(t_host - accP['t']/5 - acc['t']/5):.2f} ms")
+      f"({1e6*acc['t']/max(acc['n'], 1):.1f} us per block call), everything else {1e3*(t_host - accP['t']/5 - acc['t']/5):.2f} ms")
 ptv3.Block._native = orig
 structure.Plan.__init__ = origP
 
