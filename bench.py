@@ -271,6 +271,7 @@ def run_cuda(args):
     seg.backbone.perm_fn = None
 
     rank_ms = {}
+    step_stats = {}
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
@@ -294,7 +295,9 @@ def run_cuda(args):
         if world > 1:
             dist.barrier()
         launches = ops.launch_count()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        per_step = [a.elapsed_time(b) for a, b in evs]
+        ms = sum(per_step)
+        step_stats[fn.__name__ + ("" if fn.__name__ not in step_stats else "'")] = per_step
         prof = ops.PROFILE
         ops.PROFILE = None
         tsum = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -409,6 +412,8 @@ def run_cuda(args):
             "e2e": {"value": e2e, "unit": "points/s",
                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) + n * in_ch * 4),
                     "d2h_bytes_per_step": int(n * classes * 4), "ms_per_step": ms_e2e / args.steps},
+            "ms_per_step_median": float(np.median(step_stats["step_resident"])), "ms_per_step_min": float(np.min(step_stats["step_resident"])),
+            "ms_per_step_max": float(np.max(step_stats["step_resident"])),
             "roofline": roof, "roofline_attention": attn, "roofline_post": post, "attention_" + other: alt, "parity": None}
     if world > 1:
         line["ms_per_step_by_rank"] = rank_ms.get("step_resident")

@@ -11,7 +11,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libcdseg_b200.so")
+LIB_PATH = os.environ.get("CDSEG_LIB") or os.path.join(_HERE, "libcdseg_b200.so")      # CDSEG_LIB: an experimental build (profiles/)
 SOURCES = ["serialize.cu", "pool.cu", "conv.cu", "pointwise.cu", "attn_pack.cu", "attn_tc.cu", "attn_tc2.cu", "attn_tc3.cu", "gemm_tc.cu", "fused_post.cu", "fused_pre.cu", "block_exec.cu", "plan_exec.cu", "net_exec.cu", "losses.cu", "fragments.cu", "knn.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]

@@ -20,10 +20,11 @@ namespace tc3 {
 
 constexpr int NC = 64;                 // keys per chunk
 constexpr int NTHREADS = 192;          // 4 softmax warps + TMA producer warp + MMA issuer warp
-constexpr long long WAIT_TIMEOUT_CYCLES = 4000000000ll;
+constexpr uint32_t WAIT_TIMEOUT_POLLS = 1u << 26;
 
 template <int MODE> struct Cfg;
-template <> struct Cfg<0> {            // fp16 operands (flash-branch numerics)
+template <> struct Cfg<0> {            // fp16 operands (flash-branch numerics); P / O double-buffered, O folded one chunk late
+  static constexpr bool DEFER = true;
   static constexpr int R = 4;                          // K/V ring stages
   static constexpr int KBYTES = NC * 32;               // 64 keys x 16 d fp16
   static constexpr int VW = 32;                        // V operand width: [v | 1 | 0 x 15]
@@ -35,7 +36,23 @@ template <> struct Cfg<0> {            // fp16 operands (flash-branch numerics)
   static constexpr int TMEM_COLS = 128;
   static constexpr int COL_S = 0, COL_O0 = 64, COL_O1 = 96;
 };
-template <> struct Cfg<1> {            // hi/lo split operands (fp32-class numerics)
+#ifdef CDSEG_ATTN_TC32_DEFER           // A/B build (profiles/): mode 1 with double-buffered P / O at 2 CTAs per SM
+template <> struct Cfg<1> {
+  static constexpr bool DEFER = true;
+  static constexpr int R = 3;
+  static constexpr int KBYTES = 2 * NC * 32;
+  static constexpr int VW = 48;
+  static constexpr int VBYTES = NC * VW * 2;
+  static constexpr int STAGE = KBYTES + VBYTES;
+  static constexpr int SQ_BYTES = 2 * 128 * 32;
+  static constexpr int SP_ONE = 2 * 128 * NC * 2;
+  static constexpr int SP_BYTES = 2 * SP_ONE;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int COL_S = 0, COL_O0 = 64, COL_O1 = 128;
+};
+#else
+template <> struct Cfg<1> {            // hi/lo split operands (fp32-class numerics); P / O single-buffered, O folded in order
+  static constexpr bool DEFER = false;
   static constexpr int R = 3;
   static constexpr int KBYTES = 2 * NC * 32;           // k_hi chunk | k_lo chunk
   static constexpr int VW = 48;                        // [v_hi | 1 | 0 x 15 | v_lo]
@@ -43,10 +60,11 @@ template <> struct Cfg<1> {            // hi/lo split operands (fp32-class numer
   static constexpr int STAGE = KBYTES + VBYTES;
   static constexpr int SQ_BYTES = 2 * 128 * 32;        // q_hi | q_lo
   static constexpr int SP_ONE = 2 * 128 * NC * 2;      // P_hi | P_lo
-  static constexpr int SP_BYTES = 2 * SP_ONE;
-  static constexpr int TMEM_COLS = 256;
-  static constexpr int COL_S = 0, COL_O0 = 64, COL_O1 = 128;
+  static constexpr int SP_BYTES = SP_ONE;
+  static constexpr int TMEM_COLS = 128;
+  static constexpr int COL_S = 0, COL_O0 = 64, COL_O1 = 64;
 };
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -68,10 +86,21 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
+  // try_wait suspends the thread for a hardware-defined interval per call; counting polls instead of reading clock64 keeps the
+  // spin loop at 4 instructions (the control warps share their scheduler with softmax warps: the round-1 loop with two clock reads
+  // per poll was 20 % of all issued instructions, profiles/r02_attn_tc3_f16 hot lines)
+  uint32_t spins = 0;
   while (!mbar_try(bar, parity))
-    if (clock64() - t0 > WAIT_TIMEOUT_CYCLES) __trap();       // a protocol bug must trap, never hang
+    if (++spins > WAIT_TIMEOUT_POLLS) __trap();               // a protocol bug must trap, never hang
+}
+// control warps (TMA producer, MMA issuer) wait most of the time: back off between polls so that the spin does not take issue
+// slots from the softmax warps on the same scheduler
+__device__ __forceinline__ void mbar_wait_idle(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (sleep_ns) __nanosleep(sleep_ns);
+    if (++spins > WAIT_TIMEOUT_POLLS) __trap();
+  }
 }
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -156,10 +185,16 @@ template <int R> struct Bars {
 // DBG != 0: what-if variants for profiling ONLY (wrong results, selected by cdseg_attn_set_debug, never by the product path):
 // 1 no exponentials, 2 S read from tensor memory only for the first chunk, 3 no P stores, 4 no row max, 5 no P.V MMAs, 6 no O fold loads
 template <int MODE, int POLY, int DBG = 0>      // POLY of every 8 exponentials go to the FMA pipe (0 = all on MUFU); MODE 1 always uses MUFU
+#if defined(CDSEG_ATTN_TC32_DEFER)
 __global__ void __launch_bounds__(NTHREADS, MODE == 0 ? 3 : 2)
+#elif defined(CDSEG_ATTN_LB)
+__global__ void __launch_bounds__(NTHREADS, 3)
+#else
+__global__ void __maxnreg__(112)   // 192 threads x 112 registers: 3 CTAs (18 warps) per SM
+#endif
 attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, const __half* __restrict__ Vp,
                 const int32_t* __restrict__ patch_len, const int32_t* __restrict__ slot_dst, int H, int T, int Kp, float sl2,
-                float* __restrict__ out, int64_t out_ld) {
+                float* __restrict__ out, int64_t out_ld, uint32_t sleep_ns) {
   using C = Cfg<MODE>;
   constexpr int R = C::R;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -211,7 +246,7 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
       if (MODE == 1) tma_load_1d(smem_u32(sQ + 128 * 32), Qp + lo_off + blk16 + (int64_t)qt * 128 * 16, 128 * 32, smem_u32(&bars->q));
       for (int c = 0; c < nc; ++c) {
         const int s = c % R, u = c / R;
-        if (u > 0) mbar_wait(smem_u32(&bars->kv_empty[s]), (uint32_t)((u - 1) & 1));
+        if (u > 0) mbar_wait_idle(smem_u32(&bars->kv_empty[s]), (uint32_t)((u - 1) & 1), sleep_ns);
         uint8_t* st = sKV + s * C::STAGE;
         const uint32_t bar = smem_u32(&bars->kv_full[s]);
         mbar_expect_tx(bar, C::STAGE);
@@ -227,14 +262,14 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
       constexpr uint32_t IDESC_O = idesc(C::VW, true);           // M128 N32|48, B MN-major
       constexpr uint32_t IDESC_OL = idesc(32, true);             // MODE 1: P_lo . [v_hi | 1]
       constexpr uint32_t VKG = C::VW * 16;                       // bytes between 8-key groups of the V operand
-      mbar_wait(smem_u32(&bars->q), 0);
+      mbar_wait_idle(smem_u32(&bars->q), 0, sleep_ns);
       const uint64_t qd = make_desc(smem_u32(sQ), 128, 256);
       const uint64_t qd_lo = make_desc(smem_u32(sQ + 128 * 32), 128, 256);
       for (int g = 0; g <= nc; ++g) {
         if (g < nc) {                                            // S(g) = Q . K_g^T
           const int s = g % R;
-          mbar_wait(smem_u32(&bars->kv_full[s]), (uint32_t)((g / R) & 1));
-          if (g >= 1) mbar_wait(smem_u32(&bars->s_free), (uint32_t)((g - 1) & 1));
+          mbar_wait_idle(smem_u32(&bars->kv_full[s]), (uint32_t)((g / R) & 1), sleep_ns);
+          if (g >= 1) mbar_wait_idle(smem_u32(&bars->s_free), (uint32_t)((g - 1) & 1), sleep_ns);
           tc_fence_after();
           const uint32_t kb = smem_u32(sKV + s * C::STAGE);
           umma_f16(tmem + C::COL_S, qd, make_desc(kb, 128, 256), IDESC_S, 0);
@@ -245,8 +280,8 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
           umma_commit(smem_u32(&bars->s_full));
         }
         if (g >= 1) {                                            // [O | L](g-1) = P . [V | 1]
-          const int gp = g - 1, s = gp % R, b = gp & 1;
-          mbar_wait(smem_u32(&bars->p_full[b]), (uint32_t)((gp >> 1) & 1));
+          const int gp = g - 1, s = gp % R, b = C::DEFER ? (gp & 1) : 0;
+          mbar_wait_idle(smem_u32(&bars->p_full[b]), (uint32_t)((C::DEFER ? (gp >> 1) : gp) & 1), sleep_ns);
           tc_fence_after();
           const uint32_t vb = smem_u32(sKV + s * C::STAGE + C::KBYTES);
           const uint32_t pb = smem_u32(sP + b * C::SP_ONE);
@@ -275,8 +310,8 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
     uint8_t* prow = sP + (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
 
     auto fold = [&](int gp, float a) {                           // acc = acc * a + O_gp ; l likewise
-      const int b = gp & 1;
-      mbar_wait(smem_u32(&bars->o_full[b]), (uint32_t)((gp >> 1) & 1));
+      const int b = C::DEFER ? (gp & 1) : 0;
+      mbar_wait(smem_u32(&bars->o_full[b]), (uint32_t)((C::DEFER ? (gp >> 1) : gp) & 1));
       tc_fence_after();
       const uint32_t oc = tmem + lane_base + (b ? C::COL_O1 : C::COL_O0);
       if (MODE == 0) {
@@ -305,6 +340,9 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
     };
 
     for (int g = 0; g < nc; ++g) {
+      // in-order variant: fold O(g-1) first (before S occupies 64 registers) -- this also waits for P.V(g-1), the last reader of the
+      // single P buffer and the last writer of the single O buffer
+      if (!C::DEFER && g > 0) fold(g - 1, a_prev);
       mbar_wait(smem_u32(&bars->s_full), (uint32_t)(g & 1));
       tc_fence_after();
       uint32_t s[NC];
@@ -326,16 +364,23 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
           if (j >= valid) s[j] = 0xff800000u;                    // -inf
       }
       if (DBG == 4) mx = __uint_as_float(s[0]);
-      else {
+      else {                                                     // four independent chains: 8 dependent FMNMX3 instead of 32
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < NC; j += 2) mx = max3(mx, __uint_as_float(s[j]), __uint_as_float(s[j + 1]));
+        for (int j = 0; j < NC; j += 8) {
+          m0 = max3(m0, __uint_as_float(s[j]), __uint_as_float(s[j + 1]));
+          m1 = max3(m1, __uint_as_float(s[j + 2]), __uint_as_float(s[j + 3]));
+          m2 = max3(m2, __uint_as_float(s[j + 4]), __uint_as_float(s[j + 5]));
+          m3 = max3(m3, __uint_as_float(s[j + 6]), __uint_as_float(s[j + 7]));
+        }
+        mx = fmaxf(max3(m0, m1, m2), m3);
       }
       const float m_new = fmaxf(m, mx);
       const float msc = m_new * sl2;
       const float a_g = ex2(m * sl2 - msc);                      // first chunk: m = -inf -> 0
       m = m_new;
-      // P buffer g&1 was last read by P.V(g-2); fold(g-2) (previous iteration) waited for that product
-      uint8_t* pw = prow + (g & 1) * C::SP_ONE;
+      // deferred variant: P buffer g&1 was last read by P.V(g-2); fold(g-2) (previous iteration) waited for that product
+      uint8_t* pw = prow + (C::DEFER ? (g & 1) : 0) * C::SP_ONE;
 #pragma unroll
       for (int kg = 0; kg < NC / 8; ++kg) {
         uint32_t pk[4], pl[4];
@@ -358,8 +403,8 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
       }
       fence_async_smem();                                        // generic-proxy writes -> visible to the tensor core
       tc_fence_before();
-      mbar_arrive(smem_u32(&bars->p_full[g & 1]));
-      if (g > 0) fold(g - 1, a_prev);                            // P.V(g-1) was requested a whole chunk ago: no stall in steady state
+      mbar_arrive(smem_u32(&bars->p_full[C::DEFER ? (g & 1) : 0]));
+      if (C::DEFER && g > 0) fold(g - 1, a_prev);                // P.V(g-1) was requested a whole chunk ago: no stall in steady state
       a_prev = a_g;
     }
     fold(nc - 1, a_prev);
@@ -395,6 +440,7 @@ template <int MODE> constexpr size_t smem_bytes() {
 
 // exponentials per group of 8 computed on the FMA pipe instead of MUFU (0..3), MODE 0 only; env CDSEG_ATTN_POLY or cdseg_attn_set_poly
 static int g_attn3_debug = 0;
+static uint32_t g_attn3_sleep = [] { const char* e = getenv("CDSEG_ATTN_SLEEP"); return e ? (uint32_t)atoi(e) : 0u; }();   // ns between polls of the control warps
 CDSEG_API void cdseg_attn_set_debug(int variant) { g_attn3_debug = variant; }
 int g_cdseg_attn_poly = [] { const char* e = getenv("CDSEG_ATTN_POLY"); return e ? atoi(e) : 0; }();
 CDSEG_API void cdseg_attn_set_poly(int per8) { g_cdseg_attn_poly = per8 < 0 ? 0 : (per8 > 3 ? 3 : per8); }
@@ -426,10 +472,10 @@ CDSEG_API int cdseg_attn_tc3(const void* Q, const void* K, const void* V, const 
   const float sl2 = scale * 1.4426950408889634f;
 #define CDSEG_ATTN_LAUNCH(MODE, POLY)                                                                                      \
   tc3::attn_tc3_kernel<MODE, POLY><<<g, tc3::NTHREADS, tc3::smem_bytes<MODE>(), (cudaStream_t)stream>>>(                   \
-      (const __half*)Q, (const __half*)K, (const __half*)V, patch_len, slot_dst, H, T, Kp, sl2, out, out_ld)
+      (const __half*)Q, (const __half*)K, (const __half*)V, patch_len, slot_dst, H, T, Kp, sl2, out, out_ld, g_attn3_sleep)
 #define CDSEG_ATTN_LAUNCH_D(D)                                                                                             \
   tc3::attn_tc3_kernel<0, 0, D><<<g, tc3::NTHREADS, tc3::smem_bytes<0>(), (cudaStream_t)stream>>>(                         \
-      (const __half*)Q, (const __half*)K, (const __half*)V, patch_len, slot_dst, H, T, Kp, sl2, out, out_ld)
+      (const __half*)Q, (const __half*)K, (const __half*)V, patch_len, slot_dst, H, T, Kp, sl2, out, out_ld, g_attn3_sleep)
   if (mode == 0 && g_attn3_debug) {
     switch (g_attn3_debug) {
       case 1: CDSEG_ATTN_LAUNCH_D(1); break;

@@ -6,6 +6,10 @@
 
 #define CDSEG_API extern "C" __attribute__((visibility("default")))
 
+#ifdef CDSEG_NO_LDG   // experiment (profiles/r02_two_stream_race.md): no read-only-path (ld.global.nc) loads anywhere
+#define __ldg __ldcg
+#endif
+
 // status codes returned by every C-ABI entry point (0 == ok, >0 == cudaError_t)
 #define CDSEG_OK 0
 #define CDSEG_EINVAL (-1)      // bad argument (size / alignment / unsupported shape)

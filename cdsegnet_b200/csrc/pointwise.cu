@@ -135,6 +135,70 @@ __global__ void reduce_ln_kernel(const float* __restrict__ part, int nsplit, con
   for (int j = 0; j < VPL; ++j) { const int c = lane + 32 * j; if (c < C) ln_out[row * C + c] = (v[j] - mean) * rstd * g2[c] + b2[c]; }
 }
 
+// float4 variant for C % 128 == 0 (the C = 256 / 512 levels this kernel serves): lane owns columns 4*lane + 128*j .. +3, so a row is
+// read with G = C / 128 float4 loads per partial instead of C / 32 scalar ones -- the round-1 kernel was latency-bound (990 rows = 124
+// CTAs, 128 dependent 4-byte loads per lane: 30 us for 16 MB, profiles/r01g_launches_step_v5.md)
+template <int G>
+__global__ void reduce_ln4_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ bias, const float* __restrict__ g1,
+                                  const float* __restrict__ b1, const float* __restrict__ res, const float* __restrict__ t,
+                                  const int32_t* __restrict__ batch, const float* __restrict__ g2, const float* __restrict__ b2, float eps,
+                                  int64_t n, int C, float* __restrict__ y_out, float* __restrict__ ln_out) {
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float fc = (float)C;
+  float4 v[G];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const int c = 4 * lane + 128 * j;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int z = 0; z < nsplit; ++z) {                         // adds stay in z order (same sums as splitk_reduce)
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(part + ((int64_t)z * n + row) * C + c));
+      x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+    }
+    if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + c); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+    v[j] = x;
+    s += (x.x + x.y) + (x.z + x.w);
+  }
+  auto layer_norm = [&](const float* g, const float* b, float sum, float4* dst) {
+    const float mean = warp_sum(sum) / fc;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const float d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / fc + eps);
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int c = 4 * lane + 128 * j;
+      const float4 gg = *reinterpret_cast<const float4*>(g + c), bb = *reinterpret_cast<const float4*>(b + c);
+      dst[j] = make_float4((v[j].x - mean) * rstd * gg.x + bb.x, (v[j].y - mean) * rstd * gg.y + bb.y, (v[j].z - mean) * rstd * gg.z + bb.z,
+                           (v[j].w - mean) * rstd * gg.w + bb.w);
+    }
+  };
+  if (g1) layer_norm(g1, b1, s, v);
+  const float* tr = t ? t + (int64_t)batch[row] * C : nullptr;
+  s = 0.f;
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const int c = 4 * lane + 128 * j;
+    float4 x = v[j];
+    if (res) { const float4 r = *reinterpret_cast<const float4*>(res + row * C + c); x.x = r.x + x.x; x.y = r.y + x.y; x.z = r.z + x.z; x.w = r.w + x.w; }
+    if (tr) { const float4 r = *reinterpret_cast<const float4*>(tr + c); x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w; }
+    if (y_out) *reinterpret_cast<float4*>(y_out + row * C + c) = x;
+    v[j] = x;
+    s += (x.x + x.y) + (x.z + x.w);
+  }
+  if (!ln_out) return;
+  float4 o[G];
+  layer_norm(g2, b2, s, o);
+#pragma unroll
+  for (int j = 0; j < G; ++j) *reinterpret_cast<float4*>(ln_out + row * C + 4 * lane + 128 * j) = o[j];
+}
+
 // see include/cdseg_b200.h
 CDSEG_API int cdseg_reduce_ln(const float* part, int nsplit, const float* bias, const float* g1, const float* b1, const float* res,
                               const float* t, const int32_t* batch, const float* g2, const float* b2, float eps, int64_t n, int C,
@@ -142,6 +206,19 @@ CDSEG_API int cdseg_reduce_ln(const float* part, int nsplit, const float* bias, 
   cudaStream_t st = (cudaStream_t)stream;
   if (!part || nsplit < 1 || C <= 0 || C > 1024 || (t && !batch) || (g1 && !b1) || (ln_out && (!g2 || !b2))) return CDSEG_EINVAL;
   if (n == 0) return CDSEG_OK;
+  const bool al16 = !(((uintptr_t)part | (uintptr_t)bias | (uintptr_t)g1 | (uintptr_t)b1 | (uintptr_t)res | (uintptr_t)t | (uintptr_t)g2 |
+                        (uintptr_t)b2 | (uintptr_t)y_out | (uintptr_t)ln_out) & 15);
+  if ((C == 128 || C == 256 || C == 512) && al16) {            // 4 rows per CTA: 990 rows still give 248 CTAs
+    const int blocks4 = cdseg_div_up(n * 32, 128);
+#define LAUNCH_RL4(G) reduce_ln4_kernel<G><<<blocks4, 128, 0, st>>>(part, nsplit, bias, g1, b1, res, t, batch, g2, b2, eps, n, C, y_out, ln_out)
+    if (C == 128) LAUNCH_RL4(1);
+    else if (C == 256) LAUNCH_RL4(2);
+    else LAUNCH_RL4(4);
+#undef LAUNCH_RL4
+    CDSEG_COUNT_LAUNCH(1);
+    CDSEG_LAUNCH_CHECK();
+    return CDSEG_OK;
+  }
   const int blocks = cdseg_div_up(n * 32, 256);
 #define LAUNCH_RL(V) reduce_ln_kernel<V><<<blocks, 256, 0, st>>>(part, nsplit, bias, g1, b1, res, t, batch, g2, b2, eps, n, C, y_out, ln_out)
   if (C <= 32) LAUNCH_RL(1);

@@ -30,7 +30,10 @@ class Level:
     """One resolution level of one network: a view over a CdsegPlanLevel descriptor."""
 
     def __init__(self, plan, index, k):
-        self._plan, self._i, self._k = plan, index, k
+        # no reference to the Plan itself: Plan -> Level -> Plan would be a cycle, and a cycle keeps the (hundreds of MB) arena alive
+        # until Python's cyclic collector happens to run -- every forward would then cudaMalloc a fresh arena
+        self._mem = plan.mem
+        self._i, self._k = index, k
         self.d = plan.desc[index]
         self.parent = None
         self._cache = {}
@@ -55,7 +58,7 @@ class Level:
     def _view(self, key, ptr, shape, dtype):
         t = self._cache.get(key)
         if t is None:
-            t = self._plan.view(ptr, shape, dtype) if ptr else None
+            t = self._mem.view(ptr, shape, dtype) if ptr else None
             self._cache[key] = t
         return t
 
@@ -86,9 +89,9 @@ class Level:
     def nbr(self, ksize):
         if ksize not in self._nbr:
             if ksize == 3 and self.d.nbr3:
-                self._nbr[3] = self._plan.view(self.d.nbr3, (self.n, 27), torch.int32)
+                self._nbr[3] = self._mem.view(self.d.nbr3, (self.n, 27), torch.int32)
             elif self.d.nbr_stem and ksize == self.d.stem_ksize:
-                self._nbr[ksize] = self._plan.view(self.d.nbr_stem, (self.n, ksize ** 3), torch.int32)
+                self._nbr[ksize] = self._mem.view(self.d.nbr_stem, (self.n, ksize ** 3), torch.int32)
             else:
                 self._nbr[ksize] = ops.nbr_build(self.grid[: self.n], self.batch[: self.n], ksize)
         return self._nbr[ksize]
@@ -98,7 +101,7 @@ class Level:
         key = ("mask", ksize)
         if key not in self._nbr:
             if ksize == 3 and self.d.tile_mask3:
-                self._nbr[key] = self._plan.view(self.d.tile_mask3, ((self.n + 127) // 128,), torch.int32)
+                self._nbr[key] = self._mem.view(self.d.tile_mask3, ((self.n + 127) // 128,), torch.int32)
             else:
                 self._nbr[key] = ops.tile_tap_mask(self.nbr(ksize))
         return self._nbr[key]
@@ -109,7 +112,7 @@ class Level:
         if key not in self._nbr:
             if ksize == 3 and self.d.conv_plan3:
                 nb = int(_lib.load().cdseg_conv_plan_bytes(self.n))
-                self._nbr[key] = self._plan.view(self.d.conv_plan3, (nb,), torch.uint8)
+                self._nbr[key] = self._mem.view(self.d.conv_plan3, (nb,), torch.uint8)
             else:
                 self._nbr[key] = ops.conv_tile_plan(self.nbr(ksize))
         return self._nbr[key]
@@ -125,7 +128,7 @@ class Level:
             m = self.d.pm[order_index]
             if m.T > 0 and m.K == K and (self.d.pm_mask >> order_index) & 1:
                 T, Kp = int(m.T), int(m.Kp)
-                v = self._plan.view
+                v = self._mem.view
                 self._pm[prow] = dict(slot_src=v(m.slot_src, (T * Kp,), torch.int32), slot_dst=v(m.slot_dst, (T * Kp,), torch.int32),
                                       point_slot=v(m.point_slot, (self.n,), torch.int32), patch_len=v(m.patch_len, (T,), torch.int32),
                                       T=T, Kp=Kp, K=K, pairs=int(m.pairs))
@@ -176,6 +179,22 @@ def _draw(k, perm_fn):
 def torch_randperm(k):
     """the reference's own draw: CPU global generator (structure.py:95, ptv3.py:502)."""
     return torch.randperm(k)
+
+
+class _Mem:
+    """the plan's device arena + raw-pointer -> tensor-view conversion (shared by the Plan and its Levels)"""
+
+    def __init__(self, arena, keep):
+        self.arena, self.keep, self.base = arena, keep, arena.data_ptr()
+
+    def view(self, ptr, shape, dtype):
+        nbytes = int(np.prod(shape)) * _DT[dtype]
+        off = ptr - self.base
+        if off < 0 or off + nbytes > self.arena.numel():
+            if ptr == self.keep[1].data_ptr():
+                return self.keep[1]
+            raise _lib.CdsegError("plan pointer outside the arena")
+        return self.arena[off: off + nbytes].view(dtype).view(shape)
 
 
 class Plan:
@@ -243,7 +262,8 @@ class Plan:
         # one block from torch's caching allocator (an upper bound: the pooled sizes are only known inside the call); exported
         # Points keep lazy views into it, so it is NOT shared between plans
         self.arena = torch.empty(int(need), dtype=torch.uint8, device=dev)
-        self._base = self.arena.data_ptr()
+        self.mem = _Mem(self.arena, self._keep)
+        self._base = self.mem.base
         ids = (ctypes.c_int * k)(*[ops.ORDER_IDS[o] for o in orders])
         n_flags = extra_flags.numel() if extra_flags is not None else 0
         fh = (ctypes.c_int32 * max(n_flags, 1))()
@@ -261,10 +281,4 @@ class Plan:
 
     def view(self, ptr, shape, dtype):
         """tensor view of arena memory (or of the caller's offset tensor) at raw device pointer `ptr`"""
-        nbytes = int(np.prod(shape)) * _DT[dtype]
-        off = ptr - self._base
-        if off < 0 or off + nbytes > self.arena.numel():
-            if ptr == self._keep[1].data_ptr():
-                return self._keep[1]
-            raise _lib.CdsegError("plan pointer outside the arena")
-        return self.arena[off: off + nbytes].view(dtype).view(shape)
+        return self.mem.view(ptr, shape, dtype)

@@ -14,6 +14,7 @@ sc = synth.collate([synth.scannet_scene(120000, 0)])
 torch.manual_seed(0)
 seg = cb.build_model(configs.segmentor_cfg()); bench.random_weights(seg); seg = seg.to(DEV).eval()
 seg.backbone.attention_mode = "tc32"
+seg.backbone.overlap_streams = True
 n = len(sc["coord"])
 rng = np.random.default_rng(5)
 noise = rng.standard_normal((n, 6)).astype(np.float32)
