@@ -187,10 +187,10 @@ template <int R> struct Bars {
 template <int MODE, int POLY, int DBG = 0>      // POLY of every 8 exponentials go to the FMA pipe (0 = all on MUFU); MODE 1 always uses MUFU
 #if defined(CDSEG_ATTN_TC32_DEFER)
 __global__ void __launch_bounds__(NTHREADS, MODE == 0 ? 3 : 2)
-#elif defined(CDSEG_ATTN_LB)
-__global__ void __launch_bounds__(NTHREADS, 3)
+#elif defined(CDSEG_ATTN_MAXNREG)
+__global__ void __maxnreg__(112)   // A/B build: measured 14 % slower than the 96-register build below (profiles/r02_attention_ab.txt)
 #else
-__global__ void __maxnreg__(112)   // 192 threads x 112 registers: 3 CTAs (18 warps) per SM
+__global__ void __launch_bounds__(NTHREADS, 3)   // 96 registers, 3 CTAs (18 warps) per SM in both modes
 #endif
 attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, const __half* __restrict__ Vp,
                 const int32_t* __restrict__ patch_len, const int32_t* __restrict__ slot_dst, int H, int T, int Kp, float sl2,

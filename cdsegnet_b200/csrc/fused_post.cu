@@ -18,6 +18,7 @@
 // Warps: 0-3 row threads (operand conversion + all epilogues), 4 input loader, 5 weight loader, 6 MMA issuer / TMEM owner.
 // TMEM columns: ACC1 [0,128) fc1 chunk accumulator -> GELU'd operand | ACC0 [128,128+C) | H [128+C,128+2C) o / h operand.
 #include "fused_common.cuh"
+#include <cstdlib>
 
 namespace fz {
 
@@ -293,12 +294,13 @@ CDSEG_API int cdseg_post_attn(const float* o, const float* x1, int64_t n, int C,
     return CDSEG_EINVAL;
   fz::PostParams p;
   p.M = (int)n; p.C = C; p.ntiles = cdseg_div_up(n, fz::BM); p.eps = eps;
-  p.tmem_cols = C <= 64 ? 256 : 512;
+  static const bool excl = [] { const char* e = getenv("CDSEG_TMEM_EXCL"); return e && atoi(e) != 0; }();   // diagnostic: whole TMEM per CTA
+  p.tmem_cols = (C <= 64 && !excl) ? 256 : 512;
   p.single = g_cdseg_gemm_single;
   p.Bp_proj = reinterpret_cast<const __half*>(proj_Bp); p.Bp_fc1 = reinterpret_cast<const __half*>(fc1_Bp);
   p.Bp_fc2 = reinterpret_cast<const __half*>(fc2_Bp);
   p.b_proj = proj_b; p.ln_g = ln_g; p.ln_b = ln_b; p.b_fc1 = fc1_b; p.b_fc2 = fc2_b;
-  const int per_sm = C <= 64 ? 2 : 1;                               // TMEM: 256 columns per CTA up to C = 64, all 512 at C = 128
+  const int per_sm = (C <= 64 && !excl) ? 2 : 1;                               // TMEM: 256 columns per CTA up to C = 64, all 512 at C = 128
   size_t smem = (size_t)fz::P_SI * fz::IN_STAGE + (size_t)fz::P_SB * fz::B_STAGE + fz::P_STG + 8 * 128 * 4 + sizeof(fz::PostBars) + 1024;
   if (per_sm == 1) smem = smem > 120 * 1024 ? smem : 120 * 1024;    // keep a second CTA (blocked in tcgen05.alloc) off the SM
   static size_t configured = 0;

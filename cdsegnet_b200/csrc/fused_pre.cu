@@ -21,6 +21,7 @@
 // Warps: 0-3 row threads, 4 input loader, 5 weight loader, 6 MMA issuer / TMEM owner.
 // TMEM columns: RING / ACCq [0,128) | ACCc [128,128+C) | ACCl [128+C,128+2C).
 #include "fused_common.cuh"
+#include <cstdlib>
 #include "../../include/cdseg_b200.h"
 
 namespace fz {
@@ -531,7 +532,8 @@ CDSEG_API int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, in
     return CDSEG_EINVAL;
   fz::PreParams p;
   p.M = (int)n; p.C = C; p.ntiles = cdseg_div_up(n, fz::BM); p.eps = eps; p.nq = (3 * C + 127) / 128;
-  p.tmem_cols = C <= 64 ? 256 : 512;
+  static const bool excl = [] { const char* e = getenv("CDSEG_TMEM_EXCL"); return e && atoi(e) != 0; }();   // diagnostic: whole TMEM per CTA
+  p.tmem_cols = (C <= 64 && !excl) ? 256 : 512;
   p.nbr = nbr; p.tile_mask = tile_mask; p.plan = (const uint8_t*)plan; p.conv_in = conv_in;
   p.Bp_conv = reinterpret_cast<const __half*>(conv_Bp); p.Bp_lin = reinterpret_cast<const __half*>(lin_Bp);
   p.Bp_qkv = reinterpret_cast<const __half*>(qkv_Bp);
@@ -539,7 +541,7 @@ CDSEG_API int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, in
   p.tproj = tproj; p.batch = batch;
   p.trace = g_pre_trace; p.trace_cta = g_pre_trace_cta;
   p.single = g_cdseg_gemm_single;
-  const int per_sm = C <= 64 ? 2 : 1;
+  const int per_sm = (C <= 64 && !excl) ? 2 : 1;
   size_t smem = (size_t)fz::Q_CACHE + (size_t)fz::Q_SB * fz::B_STAGE + fz::Q_LIDX + fz::Q_PAR * 4 + sizeof(fz::PreBars) + 1024;
   if (per_sm == 1) smem = smem > 120 * 1024 ? smem : 120 * 1024;
   static size_t configured = 0;
