@@ -25,6 +25,7 @@ int pick_split(int64_t tiles, int T) {
   return T;
 }
 
+int g_net_block_limit = [] { const char* e = getenv("CDSEG_NET_BLOCK_LIMIT"); return e ? atoi(e) : 0; }();
 int g_net_debug = [] { const char* e = getenv("CDSEG_NET_DEBUG"); return e ? atoi(e) : 0; }();
 
 struct Arena {
@@ -48,9 +49,10 @@ struct Ctx {
   void* scratch; size_t scratch_bytes;   // block scratch of this branch (sized for its largest block)
   void* ws; size_t ws_bytes;             // split-K workspace for the linears outside blocks
   int ev_index;
+  int nblocks; bool skip;                // debug: stop enqueueing after g_net_block_limit blocks of this branch
 };
 
-#define RUN(call) do { if (!c.dry && c.status == CDSEG_OK) { c.status = (call); } } while (0)
+#define RUN(call) do { if (!c.dry && !c.skip && c.status == CDSEG_OK) { c.status = (call); } } while (0)
 
 // one Linear through cdseg_gemm_tc with the split heuristic of cdsegnet_b200/ptv3.py::linear / block_exec.cu::run_linear
 void linear(Ctx& c, const float* x, int64_t n, const CdsegLinW& w, const float* res, int act, float* out) {
@@ -90,6 +92,7 @@ float* block(Ctx& c, const CdsegBlockW& w, const CdsegPlanLevel& L, const float*
     return out;
   }
   if (pm.T <= 0 || !pm.slot_src) { if (c.status == CDSEG_OK) c.status = CDSEG_EINVAL; return out; }
+  if (g_net_block_limit && ++c.nblocks > g_net_block_limit) c.skip = true;
   CdsegBlockArgs b;
   memset(&b, 0, sizeof(b));
   b.n = L.n; b.C = w.C; b.H = w.H; b.T_dim = w.T_dim > 0 ? w.T_dim : 0; b.B = c.a->B;
@@ -215,7 +218,7 @@ float* cross_block(Ctx& c, const CdsegCrossW& w, const CdsegPlanLevel& Lq, const
   void* kp = c.ar->take(qk_units * unit);
   void* vp = c.ar->take(v_units * unit);
   float* o = f32(c, n, Cq);
-  if (!c.dry && c.status == CDSEG_OK) {
+  if (!c.dry && !c.skip && c.status == CDSEG_OK) {
     int64_t cnt[CDSEG_MAX_SCENES];
     for (int b = 0; b < Lq.B; ++b) cnt[b] = Lq.offset_host[b] - (b ? Lq.offset_host[b - 1] : 0);
     RUN(cdseg_patch_maps(Lk.order + (size_t)Lk.rowmap[0] * Lk.cap, cnt, Lq.B, pm.K, Kp, kv_src, kv_dst, kv_ps, kv_len, c.st));
@@ -267,8 +270,8 @@ int walk(const CdsegForwardArgs* a, bool dry, Sizes* sz) {
 
   Arena am{(char*)a->arena_main, a->arena_main_bytes, 0, 0, dry};
   Arena as_{(char*)a->arena_side, a->arena_side_bytes, 0, 0, dry};
-  Ctx cm{a, dry, CDSEG_OK, sm, &am, nullptr, 0, nullptr, 0, 0};
-  Ctx cs{a, dry, CDSEG_OK, ss, two ? &as_ : &am, nullptr, 0, nullptr, 0, 0};
+  Ctx cm{a, dry, CDSEG_OK, sm, &am, nullptr, 0, nullptr, 0, 0, 0, false};
+  Ctx cs{a, dry, CDSEG_OK, ss, two ? &as_ : &am, nullptr, 0, nullptr, 0, 0, 0, false};
   if (!dry) {
     cm.scratch_bytes = sz->scratch_m; cm.ws_bytes = sz->ws_m; cs.scratch_bytes = sz->scratch_s; cs.ws_bytes = sz->ws_s;
     cm.scratch = am.take(cm.scratch_bytes); cm.ws = am.take(cm.ws_bytes);
