@@ -463,6 +463,84 @@ __global__ void pack_b_kernel(const float* __restrict__ W, int T, int K, int N, 
   dst[NT * KC + e] = __float2half_rn(x - __half2float(h));
 }
 
+// ---- skinny Linear on the FP32 pipes: out[M, N] = act(bias + A[M, K] . W) + res for K <= 64 and many rows --------------------------
+// The level-0 linears around the blocks (grid-pool / unpool projections, proj_cat, heads: K = 32 / 64, N = 6 .. 64 (200), 120 000+ rows)
+// move 45 MB for 0.5 GFLOP: pure HBM work.  Through the tcgen05 tile kernel they took 80 us each (12 % of the HBM roofline: one
+// 128-row tile per CTA, prologue + TMEM staging + epilogue per 8 KB of input); this kernel streams them at HBM speed with exact
+// fp32 FMAs.  W is decoded from the same packed (hi | lo) operand blocks the tensor-core path uses, so callers do not change.
+// CTA = 256 threads = SK_ROWS rows x 64 columns; thread = SK_ROWS / 16 rows x 4 columns.
+constexpr int SK_COLS = 64;
+template <int K, int SK_ROWS>        // SK_ROWS = 128 (K = 32) or 64 (K = 64): x tile + W chunk stay under 48 KB of static shared memory
+__global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ A, long long lda, const __half* __restrict__ Bp, int M,
+                                                            int N, const float* __restrict__ bias, const float* __restrict__ res,
+                                                            long long ldr, int act, float* __restrict__ out, long long ldo) {
+  __shared__ float xs[SK_ROWS][K + 1];
+  __shared__ __align__(16) float ws[K][SK_COLS];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * SK_ROWS;
+  const int n0 = blockIdx.y * SK_COLS;
+  // W chunk: packed blocks [k / KC][n / NT][hi | lo][(n%NT)/8][(k%KC)/8][n%8][k%8]
+  const int ntiles = (N + NT - 1) / NT;
+  for (int i = tid; i < K * SK_COLS; i += 256) {
+    const int k = i / SK_COLS, c = i % SK_COLS, n = n0 + c;
+    float w = 0.f;
+    if (n < N) {
+      const __half* blk = Bp + ((long long)(k / KC) * ntiles + n / NT) * 2 * (NT * KC);
+      const int e = ((n % NT) / 8) * (64 * (KC / 8)) + ((k % KC) / 8) * 64 + (n % 8) * 8 + (k % 8);
+      w = __half2float(blk[e]) + __half2float(blk[NT * KC + e]);
+    }
+    ws[k][c] = w;
+  }
+  for (int i = tid; i < SK_ROWS * (K / 4); i += 256) {
+    const int r = i / (K / 4), q = i % (K / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + r < M) v = __ldcs(reinterpret_cast<const float4*>(A + (m0 + r) * lda) + q);
+    xs[r][4 * q] = v.x; xs[r][4 * q + 1] = v.y; xs[r][4 * q + 2] = v.z; xs[r][4 * q + 3] = v.w;
+  }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  constexpr int RT = SK_ROWS / 16;
+  float acc[RT][4];
+#pragma unroll
+  for (int i = 0; i < RT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) {
+    const float4 b = *reinterpret_cast<const float4*>(&ws[k][tx * 4]);
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      const float a = xs[ty * RT + i][k];
+      acc[i][0] = fmaf(a, b.x, acc[i][0]); acc[i][1] = fmaf(a, b.y, acc[i][1]);
+      acc[i][2] = fmaf(a, b.z, acc[i][2]); acc[i][3] = fmaf(a, b.w, acc[i][3]);
+    }
+  }
+  const int c = n0 + tx * 4;
+  if (c >= N) return;
+  float b4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (bias)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c + j < N) b4[j] = bias[c + j];
+  const bool vec = c + 3 < N && !(ldo & 3) && !((uintptr_t)out & 15) && (!res || (!(ldr & 3) && !((uintptr_t)res & 15)));
+#pragma unroll
+  for (int i = 0; i < RT; ++i) {
+    const long long m = m0 + ty * RT + i;
+    if (m >= M) break;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[j] = acc[i][j] + b4[j]; if (act == 1) v[j] = gelu_erf(v[j]); }
+    if (vec) {
+      if (res) { const float4 r4 = *reinterpret_cast<const float4*>(res + m * ldr + c); v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w; }
+      __stcs(reinterpret_cast<float4*>(out + m * ldo + c), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c + j < N) out[m * ldo + c + j] = v[j] + (res ? res[m * ldr + c + j] : 0.f);
+    }
+  }
+}
+
 }  // namespace gt
 
 CDSEG_API size_t cdseg_gemm_packed_b_floats(int T, int K, int N) {   // size in 4-byte units (the blocks hold fp16 pairs)
@@ -519,6 +597,16 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
     return CDSEG_EINVAL;
   if (M == 0) return CDSEG_OK;
   if (workspace_bytes < cdseg_gemm_tc_workspace_bytes(M, N, nsplit)) return CDSEG_ENOSPC;
+  // skinny Linear (K = 32 / 64, >= 16 384 rows): HBM-bound, served by the FP32-pipe streaming kernel (exact fp32 products)
+  static const bool no_skinny = [] { const char* e = getenv("CDSEG_NO_SKINNY"); return e && atoi(e) != 0; }();
+  if (!idx && T == 1 && !sub && nsplit == 1 && out && (K == 32 || K == 64) && M >= 16384 && !no_skinny && !g_cdseg_gemm_single) {
+    dim3 g(cdseg_div_up(M, K == 32 ? 128 : 64), cdseg_div_up(N, gt::SK_COLS));
+    if (K == 32) gt::skinny_linear_kernel<32, 128><<<g, 256, 0, st>>>(A, lda, reinterpret_cast<const __half*>(Bp), (int)M, N, bias, res, ldr, act, out, ldo);
+    else gt::skinny_linear_kernel<64, 64><<<g, 256, 0, st>>>(A, lda, reinterpret_cast<const __half*>(Bp), (int)M, N, bias, res, ldr, act, out, ldo);
+    CDSEG_COUNT_LAUNCH(1);
+    CDSEG_LAUNCH_CHECK();
+    return CDSEG_OK;
+  }
   // Experiment (CDSEG_GEMM_NARROW=1): a dense Linear whose caller asked for a K split (few row tiles, K >= 256) served by
   // narrower output tiles instead -- the same number of CTAs, no partial sums, no reduce launch.
   // (T, K) chunks of a contiguous row are the same operand as (1, T * K): the packed weight order [t][kc][tile] is unchanged.

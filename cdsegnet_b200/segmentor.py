@@ -48,6 +48,7 @@ class DefaultSegmentorV2(nn.Module):
         self.c_in_channels = c_in_channels
         self._dev_sched = {}
         self._t_cache = {}
+        self._pin_cache = {}
         if self.dm:
             self.eps = 1e-6
             Beta, Alpha, Alpha_bar, Sigma, SNR = self.get_diffusion_hyperparams(noise_schedule=noise_schedule, T=T,
@@ -150,6 +151,15 @@ class DefaultSegmentorV2(nn.Module):
             self._t_cache[key] = calc_t_emb(ts, self.T_dim)
         return self._t_cache[key]
 
+    def _pinned(self, shape):
+        buf = self._pin_cache.get(shape)
+        if buf is None:
+            if len(self._pin_cache) > 8:
+                self._pin_cache.clear()
+            buf = torch.empty(shape, dtype=torch.float32).pin_memory()
+            self._pin_cache[shape] = buf
+        return buf
+
     def _result(self, logits, input_dict, eval):
         if not eval:
             return dict(seg_logits=logits)
@@ -172,7 +182,9 @@ class DefaultSegmentorV2(nn.Module):
         c_feat, t = c_target, 0
         if self.dm and self.dm_input == "xt":
             if noise is None:
-                noise = torch.normal(0, 1, size=c_target.shape, dtype=torch.float32)
+                # the reference's draw (default.py:393: CPU generator, then .cuda()), written straight into a pinned staging buffer so
+                # that the host-to-device copy is a single asynchronous DMA instead of a staged pageable copy
+                noise = torch.normal(0, 1, size=c_target.shape, dtype=torch.float32, out=self._pinned(tuple(c_target.shape)))
             c_feat = noise.to(feat.device, non_blocking=True)
             t = self.T - 1
         c_point = dict(base, feat=c_feat)

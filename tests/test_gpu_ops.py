@@ -364,6 +364,27 @@ def test_gemm_tc_linear_vs_fp64(ops, lib, M, K, N, act, use_res, T, narrow):
 
 
 @pytest.mark.timeout(120)
+@pytest.mark.parametrize("M,K,N,act,use_res", [(120000, 32, 64, 0, False), (120000, 64, 20, 0, False), (120001, 64, 6, 0, False),
+                                               (52190, 64, 64, 1, True), (16384, 32, 200, 0, False), (20000, 64, 130, 1, True)])
+def test_skinny_linear_vs_fp64(ops, M, K, N, act, use_res):
+    """the level-0 linears (K = 32 / 64, >= 16 384 rows) take the FP32-pipe streaming kernel inside cdseg_gemm_tc: same contract
+    (packed operand blocks in, bias / GELU / residual fused), fp32 products -> within 2e-6 relative of fp64"""
+    gen = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=gen); w = torch.randn(N, K, generator=gen) / K ** 0.5
+    b = torch.randn(N, generator=gen); r = torch.randn(M, N, generator=gen) if use_res else None
+    ref = x.double() @ w.double().t() + b.double()
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    if use_res:
+        ref = ref + r.double()
+    Bp = ops.gemm_pack_b(w.t().contiguous()[None].to(DEV))
+    out = ops.gemm_tc(x.to(DEV), Bp, N, K, bias=b.to(DEV), res=r.to(DEV) if use_res else None, act=act)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 5e-6 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.timeout(120)
 @pytest.mark.parametrize("c,ns", [(16, 1), (32, 1), (64, 3), (96, 1), (128, 9), (256, 27)])
 def test_gemm_tc_conv_vs_oracle(ops, c, ns):
     sc = _scene((1500, 600))
