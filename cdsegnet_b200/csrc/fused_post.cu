@@ -85,7 +85,11 @@ post_kernel(const PostParams p, const __grid_constant__ CUtensorMap tmO, const _
       mbar_wait(smem_u32(&bars->in_full[s]), (in_cnt / P_SI) & 1);
       return s_in + s * IN_STAGE;
     };
-    auto in_release = [&]() { mbar_arrive(smem_u32(&bars->in_empty[in_cnt % P_SI])); ++in_cnt; };
+    // The box was read through the generic proxy (LDS) and will be overwritten through the async proxy (the next TMA load): the
+    // proxy fence orders this thread's reads before the loader's next bulk copy.  Without it the copy could land while a row's LDS
+    // were still in flight when a co-resident CTA of another stream saturated the shared-memory pipe -- 8-row groups of an output
+    // tile then picked up 16-byte chunks of the NEXT tile's input (profiles/r02_two_stream_race.md).
+    auto in_release = [&]() { fence_async_smem(); mbar_arrive(smem_u32(&bars->in_empty[in_cnt % P_SI])); ++in_cnt; };
     auto acc_wait = [&]() { mbar_wait(smem_u32(&bars->acc_done), acc_cnt & 1); ++acc_cnt; tc_fence_after(); };
     auto operand_ready = [&](int k) { tmem_st_wait(); tc_fence_before(); mbar_arrive(smem_u32(&bars->a_rdy[k])); };
 

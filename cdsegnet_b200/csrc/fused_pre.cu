@@ -108,7 +108,8 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
       mbar_wait(smem_u32(&bars->x_full[s]), (x_cnt / Q_SX) & 1);
       return s_cache + s * IN_STAGE;
     };
-    auto x_release = [&]() { mbar_arrive(smem_u32(&bars->x_empty[x_cnt % Q_SX])); ++x_cnt; };
+    // generic-proxy reads (LDS) of the box before the loader's next async-proxy write into it: proxy fence, see fused_post.cu
+    auto x_release = [&]() { fence_async_smem(); mbar_arrive(smem_u32(&bars->x_empty[x_cnt % Q_SX])); ++x_cnt; };
     auto acc_wait = [&]() { mbar_wait(smem_u32(&bars->acc_done), acc_cnt & 1); ++acc_cnt; tc_fence_after(); };
     auto operand_ready = [&](int k) { tmem_st_wait(); tc_fence_before(); mbar_arrive(smem_u32(&bars->a_rdy[k])); };
     // one [32 rows x 32 cols] box of this warp: registers -> swizzled staging -> TMA store

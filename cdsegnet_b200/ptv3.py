@@ -531,13 +531,11 @@ class PointTransformerV3(nn.Module):
         # evaluate the timestep MLP once per scene when the t_emb rows are uniform inside each scene
         # (always true for DefaultSegmentorV2: default.py:400-402, 451-454); False forces the per-point path
         self.t_emb_per_scene = True
-        # True: run the Noise Network on a second CUDA stream beside the Conditional Network.  OFF by default since round 2: with the
-        # native executor enqueueing both branches within ~1 ms, kernels of the two streams co-reside on the SMs for most of the
-        # forward and a data race shows up (a few 128-row tiles of a level-0 block output differ from run to run; every kernel pair
-        # tested in isolation is clean, compute-sanitizer memcheck is clean, single-stream runs are bit-reproducible --
-        # profiles/r02_two_stream_race.md).  The overlap was worth 2 % of the step (12.00 vs 12.25 ms), so it stays off until the
-        # root cause is found.
-        self.overlap_streams = False
+        # run the Noise Network on a second CUDA stream beside the Conditional Network (they only meet in the TransferModule): the
+        # latency-bound coarse levels of one fill the SMs the other leaves idle -- worth ~10 % of the step.  (Round 2 found and fixed
+        # the bug this schedule exposed at full overlap: a missing generic->async proxy fence in the fused kernels' input rings,
+        # profiles/r02_two_stream_race.md.)
+        self.overlap_streams = True
         self.perm_fn = None                  # tests / bench: replaces the CPU torch.randperm draws of shuffle_orders (structure.py:95, ptv3.py:502)
         self.n_cfg = dict(stride=n_stride, enc_depths=n_enc_depths, dec_depths=n_dec_depths)
         self.c_cfg = dict(stride=c_stride, enc_depths=c_enc_depths, dec_depths=c_dec_depths)
