@@ -155,3 +155,21 @@ def test_full_width_120k_scene_reduced_precision_mode(case120k):
     agree = float((got.argmax(1) == n_ref.argmax(1)).mean())
     print(f"full width, fp16 dense layers + f16 attention: max|logit - oracle| = {err:.3e}, arg-max agreement {agree:.5f}")
     assert err < 3e-2 and agree >= 0.995
+
+
+@pytest.mark.timeout(900)
+def test_two_stream_schedule_is_reproducible_at_full_width(case120k):
+    """the Noise Network on a second stream must not change a single bit: six overlapped forwards == the single-stream forward.
+    (Regression test for the round-2 race: a missing generic->async proxy fence in the fused kernels' input rings made 8-row groups of
+    level-0 block outputs pick up the next tile's data when kernels of the two streams co-resided, profiles/r02_two_stream_race.md.)"""
+    m = case120k.model
+    m.overlap_streams = False
+    try:
+        c0, n0 = case120k.cuda("tc32")
+        ref_n, ref_c = n0["feat"].clone(), c0["feat"].clone()
+        m.overlap_streams = True
+        for _ in range(6):
+            c, n = case120k.cuda("tc32")
+            assert torch.equal(n["feat"], ref_n) and torch.equal(c["feat"], ref_c)
+    finally:
+        m.overlap_streams = True
