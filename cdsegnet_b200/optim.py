@@ -27,35 +27,25 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}
 
-    def _table(self, gi, group):
-        """device table of this group's chunks; rebuilt when a gradient buffer moved (torch may re-allocate .grad)"""
-        ps = [p for p in group["params"] if p.grad is not None]
-        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr() if self.state[p] else 0,
-                     self.state[p]["exp_avg_sq"].data_ptr() if self.state[p] else 0) for p in ps)   # load_state_dict replaces the moments
-        hit = self._tables.get(gi)
-        if hit is not None and hit[0] == key:
+    def _table(self, key, ps):
+        """device table of the chunks of `ps`; rebuilt when a gradient / moment buffer moved (torch may re-allocate .grad,
+        load_state_dict replaces the moments)"""
+        sig = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(), self.state[p]["exp_avg_sq"].data_ptr()) for p in ps)
+        hit = self._tables.get(key)
+        if hit is not None and hit[0] == sig:
             return hit[1], hit[2]
         entries = []
         for p in ps:
-            if p.dtype is not torch.float32 or not p.is_cuda or not p.is_contiguous() or not p.grad.is_contiguous():
-                raise _lib.CdsegError("FusedAdamW needs contiguous fp32 CUDA parameters and gradients")
             st = self.state[p]
-            if not st:
-                st["step"] = 0
-                st["exp_avg"] = torch.zeros_like(p)
-                st["exp_avg_sq"] = torch.zeros_like(p)
             n = p.numel()
             for off in range(0, n, CHUNK):
                 b = off * 4
                 entries.append(_Entry(p.data_ptr() + b, p.grad.data_ptr() + b, st["exp_avg"].data_ptr() + b, st["exp_avg_sq"].data_ptr() + b,
                                       min(CHUNK, n - off)))
-        if not entries:
-            self._tables[gi] = (key, None, 0)
-            return None, 0
         arr = (_Entry * len(entries))(*entries)
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         dev = host.to(ps[0].device)
-        self._tables[gi] = (key, dev, len(entries))
+        self._tables[key] = (sig, dev, len(entries))
         return dev, len(entries)
 
     @torch.no_grad()
@@ -63,18 +53,29 @@ class FusedAdamW(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         lib = _lib.load()
         for gi, group in enumerate(self.param_groups):
-            table, n = self._table(gi, group)
-            if not n:
-                continue
             ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            by_step = {}
             for p in ps:
-                self.state[p]["step"] += 1
-            step = self.state[ps[0]]["step"]
+                if p.dtype is not torch.float32 or not p.is_cuda or not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise _lib.CdsegError("FusedAdamW needs contiguous fp32 CUDA parameters and gradients")
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                st["step"] += 1
+                by_step.setdefault(st["step"], []).append(p)
             b1, b2 = group["betas"]
-            check(lib.cdseg_adamw_step(table.data_ptr(), n, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                       float(group["weight_decay"]), int(step), _stream()), "adamw_step")
+            # one launch per distinct step count: the bias correction is per parameter in torch.optim.AdamW, and parameters whose
+            # gradient was None on some iterations (unused branches) lag behind the rest of their group
+            for step, sub in by_step.items():
+                table, n = self._table((gi, len(by_step) > 1 and step), sub)
+                check(lib.cdseg_adamw_step(table.data_ptr(), n, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                           float(group["weight_decay"]), int(step), _stream()), "adamw_step")
             # the kernel writes through raw pointers: tell torch the parameters changed, so that everything keyed on
-            # Parameter._version (the packed tensor-core operand caches of ptv3.py) is rebuilt before the next forward
+            # Parameter._version (the packed tensor-core operand caches of ptv3.py / netexec.py) is rebuilt before the next forward
             torch._C._increment_version(ps)
         return loss
 

@@ -221,3 +221,28 @@ def test_optimizer_step_invalidates_packed_weight_caches():
     ref = fwd(fresh.to(DEV).eval())
     assert np.abs(after - before).max() > 1e-2            # the step changed the network ...
     assert np.abs(after - ref).max() < 1e-5               # ... and the forward saw the new weights
+
+
+def test_fused_adamw_lagging_parameters_and_reloaded_state():
+    """parameters whose gradient is None on some iterations keep their own step count (per-parameter bias correction, like
+    torch.optim.AdamW), and load_state_dict -- which replaces the moment tensors -- must not leave a stale chunk table behind"""
+    from cdsegnet_b200.optim import FusedAdamW
+    torch.manual_seed(3)
+    ps = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in ((70000,), (33, 17), (5,))]
+    ref = [torch.nn.Parameter(p.detach().cpu().clone()) for p in ps]
+    opt = FusedAdamW(ps, lr=0.01, weight_decay=0.02)
+    topt = torch.optim.AdamW(ref, lr=0.01, weight_decay=0.02)
+    gen = torch.Generator().manual_seed(4)
+    for it in range(6):
+        if it == 3:                                            # checkpoint round trip: new exp_avg / exp_avg_sq tensors
+            opt.load_state_dict(opt.state_dict())
+        for i, (p, r) in enumerate(zip(ps, ref)):
+            if i == 1 and it in (1, 2, 4):                     # this parameter sits out three iterations
+                p.grad = None; r.grad = None
+                continue
+            g = torch.randn(p.shape, generator=gen)
+            p.grad = g.to(DEV); r.grad = g.clone()
+        opt.step(); topt.step()
+    torch.cuda.synchronize()
+    for p, r in zip(ps, ref):
+        assert float((p.detach().cpu() - r.detach()).abs().max()) < 2e-6
