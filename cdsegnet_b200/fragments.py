@@ -51,8 +51,8 @@ class GridSample:
         data = {k: (_dev(v, self.device) if isinstance(v, (np.ndarray, torch.Tensor)) else v) for k, v in data_dict.items()}
         data["coord"] = data["coord"].contiguous()
         p = self.plan(data["coord"])
-        if self.return_inverse:
-            data_dict["inverse"] = p["inverse"].long()
+        if self.return_inverse:                                # transform.py:873-875: set on the scene dict, so every part carries it
+            data_dict["inverse"] = data["inverse"] = p["inverse"].long()
         parts = []
         for f in range(p["n_fragments"]):
             idx = p["index"][f]

@@ -55,6 +55,19 @@ def test_plan_vs_oracle_full_size(ops, n, f64, legacy):
     assert np.array_equal(idx.cpu().numpy(), F.fragment_index(o))
 
 
+def test_return_inverse_travels_with_every_part(ops):
+    """transform.py:873-875 writes `inverse` into the scene dict inside the fragment loop, so every part (and the caller's dict)
+    carries the full-length point -> voxel map"""
+    from cdsegnet_b200.fragments import GridSample
+    gs = GridSample(grid_size=float(Z["c0_grid_size"]), hash_type=str(Z["c0_hash"]), keys=("coord",), return_inverse=True)
+    d = dict(coord=Z["c0_coord"])
+    parts = gs(d)
+    o = F.grid_sample_plan(Z["c0_coord"], float(Z["c0_grid_size"]), str(Z["c0_hash"]))
+    assert np.array_equal(d["inverse"].cpu().numpy(), o["inverse"])
+    for part in parts:
+        assert part["inverse"].shape[0] == Z["c0_coord"].shape[0] and np.array_equal(part["inverse"].cpu().numpy(), o["inverse"])
+
+
 def test_fragments_and_collect_vs_reference(ops):
     """fragment 0 through CenterShift(apply_z=False) + Collect + collate_fn == the reference's model input (its own tie order aside:
     compared on the rows both agree on)"""
