@@ -92,12 +92,15 @@ class PlanLevel(ctypes.Structure):
                 ("grid", _P), ("batch", _P), ("code", _P), ("order", _P), ("inverse", _P),
                 ("cluster", _P), ("idx_ptr", _P), ("head", _P), ("m_dev", _P), ("offset_dev", _P),
                 ("perm", _P), ("inv_perm", _P), ("o_code", _P), ("o_order", _P), ("o_inverse", _P),
-                ("nbr3", _P), ("tile_mask3", _P), ("conv_plan3", _P), ("nbr_stem", _P), ("pm", PatchMap * 4)]
+                ("nbr3", _P), ("tile_mask3", _P), ("conv_plan3", _P), ("nbr_stem", _P), ("pm", PatchMap * 4),
+                ("ready", _P), ("ready_stem", _P)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/cdseg_b200.h
 SIGNATURES = {
     "cdseg_abi_version": (_I, []),
+    "cdseg_set_pdl": (None, [_I]),
+    "cdseg_get_pdl": (_I, []),
     "cdseg_launch_count": (ctypes.c_ulonglong, []),
     "cdseg_launch_count_reset": (None, []),
     "cdseg_grid_max": (_I, [_P, _L, _P, _P]),
@@ -148,13 +151,15 @@ SIGNATURES = {
     "cdseg_conv_plan_bytes": (_Z, [_L]),
     "cdseg_conv_tile_plan": (_I, [_P, _L, _P, _P]),
     "cdseg_plan_arena_bytes": (_Z, [_L, _I, _I, _I, _I, _I, _I, _I]),
-    "cdseg_plan_build": (_I, [_P, _P, _L, _I, ctypes.POINTER(_I), _I, ctypes.POINTER(PlanLevel), _I, _P, _I, ctypes.POINTER(ctypes.c_int32), _P, _Z, _P]),
+    "cdseg_plan_finish": (_I, []),
+    "cdseg_plan_build": (_I, [_P, _P, _L, _I, ctypes.POINTER(_I), _I, ctypes.POINTER(PlanLevel), _I, _P, _I, ctypes.POINTER(ctypes.c_int32), _P, _Z, _P, _P]),
     "cdseg_net_arena_bytes": (_I, [_P, ctypes.POINTER(_Z), ctypes.POINTER(_Z)]),
     "cdseg_net_forward": (_I, [_P]),
     "cdseg_net_set_debug": (None, [_I]),
     "cdseg_struct_sizes": (_I, [ctypes.POINTER(_Z), _I]),
     "cdseg_gather_rows_pad": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "cdseg_set_fused_mask": (None, [_I]),
+    "cdseg_set_fused_ctas_per_sm": (None, [_I]),
     "cdseg_block_scratch_bytes": (_Z, [_L, _I, _I, _I, _I, _I]),
     "cdseg_block_forward": (_I, [ctypes.POINTER(BlockArgs), _P]),
     "cdseg_event_create": (_P, []),

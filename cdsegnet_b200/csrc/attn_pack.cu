@@ -27,6 +27,8 @@ __global__ void pack_heads_kernel(const float* __restrict__ src, int64_t ld, int
                                   const int32_t* __restrict__ slot_src, int H, int T, int Kp,
                                   OutT* __restrict__ dst0, OutT* __restrict__ dst1, OutT* __restrict__ dst2,
                                   int v_ones_which = -1) {
+  pdl_trigger();
+  pdl_wait();
   // consecutive threads -> consecutive slots (16-byte stores of 8 consecutive rows coalesce)
   const int64_t slots = (int64_t)T * Kp;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -88,8 +90,8 @@ CDSEG_API int cdseg_attn_pack_f16v(const float* src, int64_t ld, int col0, int C
   if (H <= 0 || C != H * 16 || nwhich < 1 || nwhich > 3 || (Kp % 128) || (ld & 3) || (col0 & 3)) return CDSEG_EINVAL;
   const int64_t total = (int64_t)T * Kp * H * nwhich;
   if (total == 0) return CDSEG_OK;
-  pack_heads_kernel<__half><<<cdseg_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      src, ld, col0, C, nwhich, slot_src, H, T, Kp, (__half*)dst0, (__half*)dst1, (__half*)dst2, v_ones ? nwhich - 1 : -1);
+  cdseg_launch_pdl(pack_heads_kernel<__half>, dim3(cdseg_div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, src, ld, col0, C, nwhich,
+                   slot_src, H, T, Kp, (__half*)dst0, (__half*)dst1, (__half*)dst2, v_ones ? nwhich - 1 : -1);
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;
@@ -102,6 +104,8 @@ CDSEG_API int cdseg_attn_pack_f16v(const float* src, int64_t ld, int col0, int C
 __global__ void pack_split_kernel(const float* __restrict__ src, int64_t ld, int col0, int C, int nwhich,
                                   const int32_t* __restrict__ slot_src, int H, int T, int Kp, __half* __restrict__ dst0,
                                   __half* __restrict__ dst1, __half* __restrict__ dst2, int v_which) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t slots = (int64_t)T * Kp;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (tid >= slots * H * nwhich) return;
@@ -150,8 +154,8 @@ CDSEG_API int cdseg_attn_pack_split(const float* src, int64_t ld, int col0, int 
   if (H <= 0 || C != H * 16 || nwhich < 1 || nwhich > 3 || (Kp % 128) || (ld & 3) || (col0 & 3)) return CDSEG_EINVAL;
   const int64_t total = (int64_t)T * Kp * H * nwhich;
   if (total == 0) return CDSEG_OK;
-  pack_split_kernel<<<cdseg_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, col0, C, nwhich, slot_src, H, T, Kp, (__half*)dst0,
-                                                                               (__half*)dst1, (__half*)dst2, has_v ? nwhich - 1 : -1);
+  cdseg_launch_pdl(pack_split_kernel, dim3(cdseg_div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, src, ld, col0, C, nwhich, slot_src,
+                   H, T, Kp, (__half*)dst0, (__half*)dst1, (__half*)dst2, has_v ? nwhich - 1 : -1);
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;

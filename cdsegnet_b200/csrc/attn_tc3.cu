@@ -199,6 +199,8 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
   constexpr int R = C::R;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int qt = blockIdx.x, t = blockIdx.y, h = blockIdx.z;
+  PDL_TRIGGER_EARLY();
+  pdl_wait();                                                    // before the first global read (patch_len may come from the kernel before the pack)
   const int len = patch_len[t];
   if (qt * 128 >= len) return;                                   // CTA-uniform: no valid query row in this tile
   const int nc = (len + NC - 1) / NC;                            // key chunks
@@ -407,6 +409,7 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
       if (C::DEFER && g > 0) fold(g - 1, a_prev);                // P.V(g-1) was requested a whole chunk ago: no stall in steady state
       a_prev = a_g;
     }
+    PDL_TRIGGER_LATE();                                          // last fold + output row left
     fold(nc - 1, a_prev);
     const int32_t dst = slot_dst[(int64_t)t * Kp + qt * 128 + r];
     if (dst >= 0) {
@@ -471,8 +474,8 @@ CDSEG_API int cdseg_attn_tc3(const void* Q, const void* K, const void* V, const 
   dim3 g(Kp / 128, T, H);
   const float sl2 = scale * 1.4426950408889634f;
 #define CDSEG_ATTN_LAUNCH(MODE, POLY)                                                                                      \
-  tc3::attn_tc3_kernel<MODE, POLY><<<g, tc3::NTHREADS, tc3::smem_bytes<MODE>(), (cudaStream_t)stream>>>(                   \
-      (const __half*)Q, (const __half*)K, (const __half*)V, patch_len, slot_dst, H, T, Kp, sl2, out, out_ld, g_attn3_sleep)
+  cdseg_launch_pdl(tc3::attn_tc3_kernel<MODE, POLY, 0>, g, dim3(tc3::NTHREADS), tc3::smem_bytes<MODE>(), (cudaStream_t)stream, \
+      (const __half*)Q, (const __half*)K, (const __half*)V, patch_len, slot_dst, H, T, Kp, sl2, out, (int64_t)out_ld, (uint32_t)g_attn3_sleep)
 #define CDSEG_ATTN_LAUNCH_D(D)                                                                                             \
   tc3::attn_tc3_kernel<0, 0, D><<<g, tc3::NTHREADS, tc3::smem_bytes<0>(), (cudaStream_t)stream>>>(                         \
       (const __half*)Q, (const __half*)K, (const __half*)V, patch_len, slot_dst, H, T, Kp, sl2, out, out_ld, g_attn3_sleep)

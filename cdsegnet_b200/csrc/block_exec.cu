@@ -22,6 +22,10 @@ struct Gemm { const float* Bp; const float* bias; };
 
 static int g_fused_mask = 0x7fffffff;
 CDSEG_API void cdseg_set_fused_mask(int mask) { g_fused_mask = mask; }
+// resident CTAs per SM of the persistent fused kernels launched from now on (0 = as many as fit).  cdseg_net_forward sets 1 around the
+// low-priority branch: its persistent CTAs then leave half of every SM to the kernels of the critical stream.
+int g_cdseg_fused_per_sm = 0;
+CDSEG_API void cdseg_set_fused_ctas_per_sm(int n) { g_cdseg_fused_per_sm = n; }
 
 // one Linear through cdseg_gemm_tc with the same split heuristic as the Python path (cdsegnet_b200/ptv3.py::linear)
 static int run_linear(const float* x, int64_t n, int K, int N, const float* Bp, const float* bias, const float* res, int act,

@@ -41,3 +41,36 @@ __device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() defau
 // kernel launch counter (bench.py's "gpu_launches" claim is read from here)
 extern unsigned long long g_cdseg_launches;
 #define CDSEG_COUNT_LAUNCH(n) (g_cdseg_launches += (n))
+
+// ---- programmatic dependent launch (PDL) ----
+// Kernels launched through cdseg_launch_pdl carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may be scheduled as soon
+// as every CTA of the preceding kernel of the stream has executed pdl_trigger() (or exited), and they must not touch global memory
+// before pdl_wait(), which returns once the preceding grid has completed and its writes are visible.  What runs before pdl_wait() --
+// barrier initialisation, TMEM allocation, descriptor prefetch -- overlaps the predecessor's tail, and the launch latency itself
+// (3.3 -> 1.2 us per dependent launch, profiles/r02_launch_gap.txt) is hidden.  Launched without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Where the trigger sits.  At the top of a kernel the dependents' CTAs become resident as early as possible -- and then hold shared memory /
+// TMEM at their pdl_wait() while the other stream could have used them (measured: 2.5 % slower forward, profiles/r02_pdl.txt).  "Late":
+// when a CTA starts its last piece of work, so the dependents only overlap the tail and the launch latency.
+#ifdef CDSEG_PDL_EARLY
+#define PDL_TRIGGER_EARLY() pdl_trigger()
+#define PDL_TRIGGER_LATE() do {} while (0)
+#else
+#define PDL_TRIGGER_EARLY() do {} while (0)
+#define PDL_TRIGGER_LATE() pdl_trigger()
+#endif
+
+extern int g_cdseg_pdl;                     // serialize.cu; env CDSEG_PDL=0 disables the attribute
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t cdseg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_cdseg_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

@@ -53,6 +53,7 @@ post_kernel(const PostParams p, const __grid_constant__ CUtensorMap tmO, const _
   const int C = p.C, nc = C / KC, J = nc;                        // J hidden chunks of 128 = 4C / 128
   float* s_bp = s_par; float* s_g = s_par + C; float* s_be = s_par + 2 * C; float* s_b2 = s_par + 3 * C; float* s_b1 = s_par + 4 * C;
 
+  PDL_TRIGGER_EARLY();
   if (threadIdx.x == 0) {
     for (int s = 0; s < P_SI; ++s) { mbar_init(smem_u32(&bars->in_full[s]), 1); mbar_init(smem_u32(&bars->in_empty[s]), 128); }
     for (int s = 0; s < P_SB; ++s) { mbar_init(smem_u32(&bars->b_full[s]), 1); mbar_init(smem_u32(&bars->b_empty[s]), 1); }
@@ -68,6 +69,7 @@ post_kernel(const PostParams p, const __grid_constant__ CUtensorMap tmO, const _
                  "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();                 // everything above read parameters only (never written during a forward); every thread waits here
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -94,6 +96,7 @@ post_kernel(const PostParams p, const __grid_constant__ CUtensorMap tmO, const _
     auto operand_ready = [&](int k) { tmem_st_wait(); tc_fence_before(); mbar_arrive(smem_u32(&bars->a_rdy[k])); };
 
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      if (tile + (int)gridDim.x >= p.ntiles) PDL_TRIGGER_LATE();      // this CTA's last tile
       float v[32];
       // ---- o tile -> A operand of GEMM0 (proj)
       for (int kc = 0; kc < nc; ++kc) {
@@ -278,6 +281,7 @@ int cdseg_make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64
 }
 
 extern int g_cdseg_gemm_single;                  // gemm_tc.cu
+extern int g_cdseg_fused_per_sm;                 // block_exec.cu
 
 static int sm_count() {
   static int n = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
@@ -313,8 +317,9 @@ CDSEG_API int cdseg_post_attn(const float* o, const float* x1, int64_t n, int C,
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  const int grid = p.ntiles < per_sm * sm_count() ? p.ntiles : per_sm * sm_count();
-  fz::post_kernel<<<grid, fz::P_THREADS, smem, (cudaStream_t)stream>>>(p, tmO, tmX, tmY);
+  const int per_sm_run = (g_cdseg_fused_per_sm > 0 && g_cdseg_fused_per_sm < per_sm) ? g_cdseg_fused_per_sm : per_sm;
+  const int grid = p.ntiles < per_sm_run * sm_count() ? p.ntiles : per_sm_run * sm_count();
+  cdseg_launch_pdl(fz::post_kernel, dim3(grid), dim3(fz::P_THREADS), smem, (cudaStream_t)stream, p, tmO, tmX, tmY);
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;

@@ -71,6 +71,7 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
   float *s_bc = s_par, *s_bl = s_par + C, *s_cg = s_par + 2 * C, *s_cb = s_par + 3 * C, *s_g1 = s_par + 4 * C, *s_b1 = s_par + 5 * C,
         *s_bq = s_par + 6 * C;
 
+  PDL_TRIGGER_EARLY();
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars->fill_full), 1);
     mbar_init(smem_u32(&bars->cache_free), 128);
@@ -91,6 +92,7 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
                  "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();                 // everything above read parameters only (never written during a forward); every thread waits here
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -128,6 +130,7 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
 #define STAMP(k) do { if (tr && tn < 6) p.trace[tn * 12 + (k)] = clock64(); } while (0)
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tn) {
       STAMP(0);
+      if (tile + (int)gridDim.x >= p.ntiles) PDL_TRIGGER_LATE();      // this CTA's last tile
       const long long m = (long long)tile * BM + r;
       const int row0 = tile * BM + warp * 32;
       const int U = __ldg(reinterpret_cast<const int*>(p.plan + (size_t)tile * Q_REC));
@@ -499,6 +502,7 @@ __global__ void __launch_bounds__(BM) conv_tile_plan_kernel(const int32_t* __res
 static long long* g_pre_trace = nullptr;
 static int g_pre_trace_cta = 0;
 extern int g_cdseg_gemm_single;                  // gemm_tc.cu
+extern int g_cdseg_fused_per_sm;                 // block_exec.cu
 CDSEG_API void cdseg_pre_attn_set_trace(long long* buf, int cta) { g_pre_trace = buf; g_pre_trace_cta = cta; }
 
 static int sm_count_pre() {
@@ -551,8 +555,9 @@ CDSEG_API int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, in
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  const int grid = p.ntiles < per_sm * sm_count_pre() ? p.ntiles : per_sm * sm_count_pre();
-  fz::pre_kernel<<<grid, fz::Q_THREADS, smem, (cudaStream_t)stream>>>(p, tmG, tmX, tmX1, tmQ);
+  const int per_sm_run = (g_cdseg_fused_per_sm > 0 && g_cdseg_fused_per_sm < per_sm) ? g_cdseg_fused_per_sm : per_sm;
+  const int grid = p.ntiles < per_sm_run * sm_count_pre() ? p.ntiles : per_sm_run * sm_count_pre();
+  cdseg_launch_pdl(fz::pre_kernel, dim3(grid), dim3(fz::Q_THREADS), smem, (cudaStream_t)stream, p, tmG, tmX, tmX1, tmQ);
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;

@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
   const int un = (wn + 15) & ~15;                   // UMMA N (multiple of 16)
   const int kch = (p.K + KC - 1) / KC;
   const int t_begin = (int)((long long)p.T * z / p.nsplit), t_end = (int)((long long)p.T * (z + 1) / p.nsplit);
-  const uint32_t mask = p.tile_mask ? p.tile_mask[tile_m] : 0xffffffffu;
 
+  PDL_TRIGGER_EARLY();
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_RING; ++s) {
       mbar_init(smem_u32(&bars->full_a[s]), 128);
@@ -165,6 +165,14 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
     mbar_init(smem_u32(&bars->acc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();                                     // nothing above touches global memory
+  const uint32_t mask = p.tile_mask ? p.tile_mask[tile_m] : 0xffffffffu;
   int ntap = t_end - t_begin;
   if (p.T <= 32) {
     const uint32_t width = (uint32_t)(t_end - t_begin);
@@ -174,12 +182,6 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
       int n = 0;
       for (uint32_t m = present; m; m &= m - 1) bars->taps[n++] = (uint8_t)(__ffs(m) - 1);
     }
-  }
-  if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)),
-                 "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
     // TMEM (lane == row) -> registers -> bias/GELU -> shared-memory staging (each warp only touches its own
     // 32 rows, so __syncwarp suffices) -> coalesced 128-byte row segments to HBM (+ residual, read coalesced).
     if (tr && threadIdx.x == 0) p.trace[4] = clock64();                  // producer loop done
+    PDL_TRIGGER_LATE();                                                  // only the last MMAs and the epilogue are left
     if (n_iter > 0) {
       mbar_wait(smem_u32(&bars->acc), 0);
       tc_fence_after();
@@ -414,6 +417,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int nsplit, long long M, int N,
                                      const float* __restrict__ bias, const float* __restrict__ res, long long ldr,
                                      int act, float* __restrict__ out, long long ldo) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= M * N) return;
   const long long m = i / N;
@@ -648,12 +653,12 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + nw - 1) / nw, nsplit);
-  if (dense3) gt::gemm_tc_kernel<3><<<g, gt::NTHREADS, smem, st>>>(p);
-  else gt::gemm_tc_kernel<2><<<g, gt::NTHREADS, smem, st>>>(p);
+  if (dense3) cdseg_launch_pdl(gt::gemm_tc_kernel<3>, g, dim3(gt::NTHREADS), smem, st, p);
+  else cdseg_launch_pdl(gt::gemm_tc_kernel<2>, g, dim3(gt::NTHREADS), smem, st, p);
   CDSEG_COUNT_LAUNCH(1);
   if (nsplit > 1 && out) {                   // out == NULL: the caller consumes the raw partials part[z][M][N] itself (cdseg_reduce_ln)
-    gt::splitk_reduce_kernel<<<cdseg_div_up(M * N, 256), 256, 0, st>>>((const float*)workspace, nsplit, M, N, bias, res,
-                                                                       ldr, act, out, ldo);
+    cdseg_launch_pdl(gt::splitk_reduce_kernel, dim3(cdseg_div_up(M * N, 256)), dim3(256), 0, st, (const float*)workspace, nsplit,
+                     (long long)M, N, bias, res, (long long)ldr, act, out, (long long)ldo);
     CDSEG_COUNT_LAUNCH(1);
   }
   CDSEG_LAUNCH_CHECK();

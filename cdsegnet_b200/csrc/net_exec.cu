@@ -26,6 +26,7 @@ int pick_split(int64_t tiles, int T) {
 }
 
 int g_net_block_limit = [] { const char* e = getenv("CDSEG_NET_BLOCK_LIMIT"); return e ? atoi(e) : 0; }();
+int g_side_per_sm = [] { const char* e = getenv("CDSEG_SIDE_CTAS"); return e ? atoi(e) : 0; }();
 int g_net_debug = [] { const char* e = getenv("CDSEG_NET_DEBUG"); return e ? atoi(e) : 0; }();
 
 struct Arena {
@@ -53,6 +54,9 @@ struct Ctx {
 };
 
 #define RUN(call) do { if (!c.dry && !c.skip && c.status == CDSEG_OK) { c.status = (call); } } while (0)
+
+// plan built with an aux stream: the indice tables of a level are complete once its `ready` event has fired (include/cdseg_b200.h)
+inline void need(Ctx& c, void* ev) { if (!c.dry && ev) cudaStreamWaitEvent(c.st, (cudaEvent_t)ev, 0); }
 
 // one Linear through cdseg_gemm_tc with the split heuristic of cdsegnet_b200/ptv3.py::linear / block_exec.cu::run_linear
 void linear(Ctx& c, const float* x, int64_t n, const CdsegLinW& w, const float* res, int act, float* out) {
@@ -110,13 +114,21 @@ float* block(Ctx& c, const CdsegBlockW& w, const CdsegPlanLevel& L, const float*
   if (c.a->block_events)
     for (int i = 0; i < 6; ++i) b.ev[i] = c.a->block_events[(size_t)c.ev_index * 6 + i];
   ++c.ev_index;
+  // low-priority branch next to the critical one: one persistent CTA per SM, so the critical stream's kernels always find room
+  const bool yield = c.a->stream_side && c.st == (cudaStream_t)c.a->stream_side && c.st != (cudaStream_t)c.a->stream_main && g_side_per_sm > 0;
+  if (yield) cdseg_set_fused_ctas_per_sm(g_side_per_sm);
   RUN(cdseg_block_forward(&b, c.st));
+  if (yield) cdseg_set_fused_ctas_per_sm(0);
   return out;
 }
 
 // encoder stage: [SerializedPooling] + blocks.  x: features of the parent level (stage > 0) or of this level (stage 0)
 float* enc_stage(Ctx& c, const CdsegStageW& s, const CdsegPlanLevel* lv, int base, const float* x, const float* t_scene) {
   const CdsegPlanLevel& L = lv[base + s.level];
+  if (L.parent >= 0 && !c.dry) {                          // first pooled stage: the plan's deferred launches go out now (include/cdseg_b200.h)
+    const int r = cdseg_plan_finish();
+    if (r != CDSEG_OK && c.status == CDSEG_OK) c.status = r;
+  }
   if (s.has_pool) {
     const CdsegPlanLevel& P = lv[L.parent];
     float* p = f32(c, P.n, s.pool.proj.N);
@@ -127,6 +139,7 @@ float* enc_stage(Ctx& c, const CdsegStageW& s, const CdsegPlanLevel* lv, int bas
                           nullptr, c.st));
     x = f;
   }
+  need(c, L.ready);
   for (int i = 0; i < s.n_blocks; ++i) x = block(c, s.blocks[i], L, x, nullptr, t_scene);
   return (float*)x;
 }
@@ -155,6 +168,7 @@ float* dec_stage(Ctx& c, const CdsegStageW& s, const CdsegPlanLevel* lv, int bas
   // reference quirk (ptv3.py:608-625): parent.sparse_conv_feat keeps the unscaled proj_skip output, so the FIRST block's CPE
   // convolves `skip`, not the fused features
   const float* x = feat;
+  need(c, L.ready);
   for (int i = 0; i < s.n_blocks; ++i) x = block(c, s.blocks[i], L, x, i == 0 ? skip : nullptr, t_scene);
   return (float*)x;
 }
@@ -164,6 +178,7 @@ float* stem(Ctx& c, const CdsegStemW& w, const CdsegPlanLevel& L0, const float* 
   RUN(cdseg_gather_rows_pad(feat_caller, L0.perm, L0.n, w.cin, 8, x8, c.st));
   float* out = f32(c, L0.n, w.cout);
   const int taps = w.ksize * w.ksize * w.ksize;
+  need(c, L0.ready_stem);
   RUN(cdseg_conv_im2col_tc(x8, L0.nbr_stem, taps, w.Bp, L0.n, w.cout, w.shift, 1, out, w.cout, c.st));
   return out;
 }
@@ -185,21 +200,30 @@ float* cpe(Ctx& c, const float* x, const CdsegPlanLevel& L, int C, const float* 
   return y1;
 }
 
-// CrossBlock (ptv3.py:1179-1223): q = CN features at its last level, kv = NN features at its last level.  *kv_out = LN(kv) (the
-// reference leaves it in kv_point.feat, ptv3.py:1190-1192).  Returns the new q features.
-float* cross_block(Ctx& c, const CdsegCrossW& w, const CdsegPlanLevel& Lq, const CdsegPlanLevel& Lk, const float* xq, const float* xkv,
-                   float** kv_out) {
+// CrossBlock (ptv3.py:1179-1223): q = features of the 5-stage network at its last level, kv = features of the 3-stage network at its
+// last level.  The kv half -- kv_point.feat = LN(kv + cpe(kv)), which the reference leaves in kv_point.feat (ptv3.py:1190-1192) and the
+// 3-stage decoder then consumes -- depends on the 3-stage encoder only, so it runs on that network's stream and its decoder never waits
+// for the 5-stage encoder (profiles/r02_timeline.md: that wait idled the side stream for 3 ms while the main stream ran its
+// latency-bound deep levels on a mostly empty GPU).
+float* cross_kv(Ctx& c, const CdsegCrossW& w, const CdsegPlanLevel& Lk, const float* xkv) {
+  const int Ck = w.Ckv;
+  need(c, Lk.ready);
+  float* ck = cpe(c, xkv, Lk, Ck, w.kv_conv_Bp, w.kv_conv_b, w.kv_lin, w.kv_cpe_ln, w.ln_eps);
+  float* hkv = f32(c, Lk.n, Ck);
+  RUN(cdseg_add_layernorm(xkv, ck, nullptr, nullptr, w.kv_norm1.g, w.kv_norm1.b, w.ln_eps, Lk.n, Ck, nullptr, hkv, c.st));
+  return hkv;
+}
+
+// the q half: returns the new q features.  hkv = cross_kv's result (ordered by the caller's event when it comes from another stream)
+float* cross_block(Ctx& c, const CdsegCrossW& w, const CdsegPlanLevel& Lq, const CdsegPlanLevel& Lk, const float* xq, const float* hkv) {
   if (!c.dry && Lq.n != Lk.n) { if (c.status == CDSEG_OK) c.status = CDSEG_EINVAL; }     // ptv3.py:1008-1010 index kv with q's pad map
   const int64_t n = Lq.n;
-  const int Cq = w.Cq, Ck = w.Ckv, H = w.H;
+  const int Cq = w.Cq, H = w.H;
+  need(c, Lq.ready); need(c, Lk.ready);
   float* cq = cpe(c, xq, Lq, Cq, w.q_conv_Bp, w.q_conv_b, w.q_lin, w.q_cpe_ln, w.ln_eps);
   float* q1 = f32(c, n, Cq);
   float* hq = f32(c, n, Cq);
   RUN(cdseg_add_layernorm(xq, cq, nullptr, nullptr, w.q_norm1.g, w.q_norm1.b, w.ln_eps, n, Cq, q1, hq, c.st));
-  float* ck = cpe(c, xkv, Lk, Ck, w.kv_conv_Bp, w.kv_conv_b, w.kv_lin, w.kv_cpe_ln, w.ln_eps);
-  float* hkv = f32(c, Lk.n, Ck);
-  RUN(cdseg_add_layernorm(xkv, ck, nullptr, nullptr, w.kv_norm1.g, w.kv_norm1.b, w.ln_eps, Lk.n, Ck, nullptr, hkv, c.st));
-  *kv_out = hkv;
   float* Q = f32(c, n, Cq);
   linear(c, hq, n, w.q, nullptr, 0, Q);
   float* KV = f32(c, Lk.n, 2 * Cq);
@@ -289,11 +313,17 @@ int walk(const CdsegForwardArgs* a, bool dry, Sizes* sz) {
 
   if (two && !dry) { cudaEventRecord(g_ev[0], sm); cudaStreamWaitEvent(ss, g_ev[0], 0); }     // plan tables were built on the main stream
 
-  // ---- Noise Network encoder (side stream) ----
+  // Enqueue order.  The 5-stage network is the critical path, so with two streams its kernels are enqueued first: the host needs
+  // ~0.25 ms to enqueue the 3-stage encoder, which used to delay the first kernel of the critical stream by as much
+  // (profiles/r02_timeline.md).  One stream (and the debug serialisations) keep the historical order.
+  const bool main_first = two && !(g_net_debug & 3);
   float* cx = nullptr;
+  float* cx_kv = nullptr;
   float* t_scene = nullptr;
   float* c_skip[CDSEG_MAX_STAGES] = {nullptr};
-  if (w.condition) {
+  float* n_skip[CDSEG_MAX_STAGES] = {nullptr};
+  float* nx = nullptr;
+  auto side_encoder = [&]() {                             // ---- 3-stage network: timestep MLP, stem, encoder (side stream) ----
     Ctx& c = cs;
     if (w.T_dim > 0 && a->t_emb) {                        // timestep MLP once per scene (ptv3.py:1772-1778): fc_t1 -> swish -> fc_t2 -> swish
       float* t1 = f32(c, a->B, 4 * w.T_dim);
@@ -303,31 +333,37 @@ int walk(const CdsegForwardArgs* a, bool dry, Sizes* sz) {
     }
     cx = stem(c, w.c_stem, lv[cb], a->c_feat);
     for (int s = 0; s < w.c_enc; ++s) { cx = enc_stage(c, w.c_enc_st[s], lv, cb, cx, t_scene); c_skip[s] = cx; }
+    cx = cx_kv = cross_kv(c, w.tm, lv[cb + w.c_enc - 1], cx);     // TransferModule, kv half: the decoder below starts from it
     if (two && !dry) cudaEventRecord(g_ev[1], ss);
     if (two && !dry && (g_net_debug & 1)) cudaStreamWaitEvent(sm, g_ev[1], 0);          // debug: serialise the two encoders
-  }
-  // ---- Conditional Network encoder (main stream) ----
-  float* n_skip[CDSEG_MAX_STAGES] = {nullptr};
-  float* nx = stem(cm, w.n_stem, lv[nb], a->n_feat);
-  for (int s = 0; s < w.n_enc; ++s) { nx = enc_stage(cm, w.n_enc_st[s], lv, nb, nx, nullptr); n_skip[s] = nx; }
-  if (w.condition) {
-    // ---- TransferModule (main stream) ----
-    if (two && !dry) cudaStreamWaitEvent(sm, g_ev[1], 0);
-    float* kv_new = nullptr;
-    nx = cross_block(cm, w.tm, lv[nb + w.n_enc - 1], lv[cb + w.c_enc - 1], nx, cx, &kv_new);
-    cx = kv_new;
-    if (two && !dry) { cudaEventRecord(g_ev[2], sm); cudaStreamWaitEvent(ss, g_ev[2], 0); }
-    // ---- Noise Network decoder + head (side stream) ----
+  };
+  auto main_encoder = [&]() {                             // ---- 5-stage network: stem, encoder (main stream) ----
+    nx = stem(cm, w.n_stem, lv[nb], a->n_feat);
+    for (int s = 0; s < w.n_enc; ++s) { nx = enc_stage(cm, w.n_enc_st[s], lv, nb, nx, nullptr); n_skip[s] = nx; }
+  };
+  auto side_decoder = [&]() {                             // ---- 3-stage network: decoder + head (side stream) ----
     Ctx& c = cs;
     for (int j = 0; j < w.c_dec; ++j) cx = dec_stage(c, w.c_dec_st[j], lv, cb, cx, c_skip[w.c_dec_st[j].level], t_scene);
     head(c, w.c_head, lv[cb], cx, a->c_out);
     if (two && !dry) cudaEventRecord(g_ev[3], ss);
     if (two && !dry && (g_net_debug & 2)) cudaStreamWaitEvent(sm, g_ev[3], 0);          // debug: serialise the two decoders
+  };
+  auto main_decoder = [&]() {                             // ---- 5-stage network: decoder + head (main stream) ----
+    for (int j = 0; j < w.n_dec; ++j) nx = dec_stage(cm, w.n_dec_st[j], lv, nb, nx, n_skip[w.n_dec_st[j].level], nullptr);
+    head(cm, w.n_head, lv[nb], nx, a->n_out);
+  };
+  if (!w.condition) {
+    main_encoder();
+    main_decoder();
+  } else {
+    // the 3-stage network never waits for the 5-stage one: encoder, kv half of the TransferModule and decoder are one chain
+    if (main_first) { main_encoder(); side_encoder(); side_decoder(); } else { side_encoder(); side_decoder(); main_encoder(); }
+    // ---- TransferModule, q half (main stream) ----
+    if (two && !dry) cudaStreamWaitEvent(sm, g_ev[1], 0);
+    nx = cross_block(cm, w.tm, lv[nb + w.n_enc - 1], lv[cb + w.c_enc - 1], nx, cx_kv);
+    main_decoder();
+    if (two && !dry) cudaStreamWaitEvent(sm, g_ev[3], 0);
   }
-  // ---- Conditional Network decoder + head (main stream) ----
-  for (int j = 0; j < w.n_dec; ++j) nx = dec_stage(cm, w.n_dec_st[j], lv, nb, nx, n_skip[w.n_dec_st[j].level], nullptr);
-  head(cm, w.n_head, lv[nb], nx, a->n_out);
-  if (two && !dry) cudaStreamWaitEvent(sm, g_ev[3], 0);
 
   if (dry) {
     sz->act_m = am.high; sz->act_s = as_.high;

@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "../../include/cdseg_b200.h"
 #include <cstring>
+#include <functional>
+#include <vector>
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -39,7 +41,7 @@ CDSEG_API size_t cdseg_plan_arena_bytes(int64_t N, int B, int k, int n_levels, i
   const size_t w2 = cdseg_pool_plan_workspace_bytes(k, N), w3 = cdseg_nbr_workspace_bytes(N);
   ws = ws > w2 ? ws : w2;
   ws = ws > w3 ? ws : w3;
-  return s + al256(ws) + (1 << 16);
+  return s + al256(ws) + al256(w3) + (1 << 16);                     // + the aux stream's hash workspace
 }
 
 // host staging for the two device->host copies (pinned, grown on demand)
@@ -54,14 +56,47 @@ static void* stage(size_t bytes) {
   return g_stage;
 }
 
+// events of the aux-stream schedule: one per level (tables complete), one for the stem table, two forks.  Static: a later plan's
+// records land later on the same in-order aux stream, so a consumer that waits on a re-recorded event only over-waits.
+enum { MAX_LV = 16 };
+static cudaEvent_t g_pev[MAX_LV + 3] = {};
+static bool plan_events() {
+  for (auto& e : g_pev)
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+  return true;
+}
+
+// Launches of the pooled levels' tables and slot maps that an aux-stream build leaves for cdseg_plan_finish(): after the second host sync
+// the GPU is waiting for the host, and these ~60 launches (0.25 ms of enqueue time) feed nothing before the second stage of either
+// network -- cdseg_net_forward enqueues the stems and the level-0 stage first and calls cdseg_plan_finish() before its first pooled
+// stage (profiles/r02_timeline.md).  One plan at a time per process (the list is static); a new build flushes what is left.
+static std::vector<std::function<int()>> g_pending;
+CDSEG_API int cdseg_plan_finish(void) {
+  int rc = CDSEG_OK;
+  for (auto& f : g_pending) {
+    const int r = f();
+    if (rc == CDSEG_OK) rc = r;
+  }
+  g_pending.clear();
+  return rc;
+}
+
 // levels[0 .. n_lv): every level of both networks.  Inputs per level (host): parent (index of the level it is pooled from, -1 for a
 // level-0 entry), stride, rowmap (logical curve row -> physical row), K + pm_mask (patch maps wanted, by logical curve), want_*.
 // Level-0 entries share one set of arrays (the two networks serialize the same points).  A parent must precede its children.
 CDSEG_API int cdseg_plan_build(const int32_t* grid, const int64_t* offset, int64_t N, int B, const int* order_ids, int k,
                                CdsegPlanLevel* lv, int n_lv, const int32_t* extra_flags, int n_flags, int32_t* flags_host,
-                               void* arena, size_t arena_bytes, void* stream) {
-  if (!grid || !offset || N <= 0 || B <= 0 || B > CDSEG_MAX_SCENES || k <= 0 || k > 4 || !lv || n_lv <= 0 || !arena) return CDSEG_EINVAL;
+                               void* arena, size_t arena_bytes, void* stream, void* aux_stream) {
+  if (!grid || !offset || N <= 0 || B <= 0 || B > CDSEG_MAX_SCENES || k <= 0 || k > 4 || !lv || n_lv <= 0 || n_lv > MAX_LV || !arena)
+    return CDSEG_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
+  // aux stream: the indice tables (60 % of the plan phase's device time) only feed the feature phase, so they are built beside the
+  // pooling hierarchy and beside the first kernels of the forward; consumers wait on the per-level `ready` events.
+  const bool two = aux_stream && aux_stream != stream;
+  cudaStream_t sa = two ? (cudaStream_t)aux_stream : st;
+  if (two && !plan_events()) return (int)cudaErrorUnknown;
+  if (!g_pending.empty()) { const int r = cdseg_plan_finish(); if (r != CDSEG_OK) return r; }
+  bool defer = false;                                              // set after the second sync (pooled levels only)
   char* p = (char*)arena;
   char* const end = p + arena_bytes;
   bool oom = false;
@@ -128,6 +163,7 @@ CDSEG_API int cdseg_plan_build(const int32_t* grid, const int64_t* offset, int64
     CdsegPlanLevel& L = lv[i];
     L.B = B;
     L.cap = N;
+    L.ready = L.ready_stem = nullptr;
     if (L.parent < 0) {
       L.n = N; L.depth = depth; L.c0 = -1; L.pooling_depth = 0;
       L.grid = i_grid; L.batch = i_batch; L.code = i_code; L.order = i_order; L.inverse = i_inverse;
@@ -136,6 +172,56 @@ CDSEG_API int cdseg_plan_build(const int32_t* grid, const int64_t* offset, int64
       memcpy(L.offset_host, off_host, (size_t)B * 8);
     }
   }
+  // ---------------- tables: neighbour indices, tap masks, conv tile plans (aux stream when given) ----------------
+  const size_t ws_a_bytes = two ? cdseg_nbr_workspace_bytes(N) : ws_bytes;
+  void* ws_a = two ? take(ws_a_bytes) : ws;
+  if (oom) return CDSEG_ENOSPC;
+  int first0 = -1;
+  auto build_tables = [&](int i) -> int {
+    CdsegPlanLevel& L = lv[i];
+    if (L.parent < 0 && first0 >= 0) {                               // the second network's level 0: same points, same tables
+      const CdsegPlanLevel& F = lv[first0];
+      L.nbr3 = F.nbr3; L.tile_mask3 = F.tile_mask3; L.conv_plan3 = F.conv_plan3; L.nbr_stem = F.nbr_stem;
+      L.ready = F.ready; L.ready_stem = F.ready_stem;
+      return CDSEG_OK;
+    }
+    if (L.parent < 0) first0 = i;
+    const int64_t n = L.n;
+    L.nbr3 = (int32_t*)take((size_t)n * 27 * 4);
+    L.tile_mask3 = (uint32_t*)take(((size_t)n / 128 + 1) * 4);
+    L.conv_plan3 = nullptr;
+    L.nbr_stem = nullptr;
+    bool want_plan = L.want_conv_plan != 0, want_stem = L.stem_ksize > 0;
+    if (L.parent < 0)
+      for (int j = i + 1; j < n_lv; ++j)
+        if (lv[j].parent < 0) { want_plan |= lv[j].want_conv_plan != 0; want_stem |= lv[j].stem_ksize > 0; }
+    if (want_plan) L.conv_plan3 = take(cdseg_conv_plan_bytes(n));
+    const int sk = L.stem_ksize > 0 ? L.stem_ksize : 5;
+    if (want_stem) L.nbr_stem = (int32_t*)take((size_t)n * sk * sk * sk * 4);
+    if (oom) return CDSEG_ENOSPC;
+    if (two) { L.ready = g_pev[i]; if (L.nbr_stem) L.ready_stem = g_pev[MAX_LV]; }
+    const CdsegPlanLevel D = L;                                      // by value: the closure may run after this call has returned
+    cudaEvent_t ev = two ? g_pev[i] : nullptr, ev_stem = two ? g_pev[MAX_LV] : nullptr;
+    auto launches = [D, n, sk, ws_a, ws_a_bytes, sa, ev, ev_stem]() -> int {
+      int st_;
+      if (n > 0) {
+        if (D.nbr_stem) {                                            // first: the stems are the first consumers
+          RUN(cdseg_nbr_build(D.grid, D.batch, n, sk, D.nbr_stem, ws_a, ws_a_bytes, sa));
+          if (ev_stem) cudaEventRecord(ev_stem, sa);
+        }
+        RUN(cdseg_nbr_build(D.grid, D.batch, n, 3, D.nbr3, ws_a, ws_a_bytes, sa));
+        RUN(cdseg_tile_tap_mask(D.nbr3, n, 27, D.tile_mask3, sa));
+        if (D.conv_plan3) RUN(cdseg_conv_tile_plan(D.nbr3, n, D.conv_plan3, sa));
+      }
+      if (ev) cudaEventRecord(ev, sa);
+      return CDSEG_OK;
+    };
+    if (defer) { g_pending.push_back(launches); return CDSEG_OK; }
+    return launches();
+  };
+  if (two) { cudaEventRecord(g_pev[MAX_LV + 1], st); cudaStreamWaitEvent(sa, g_pev[MAX_LV + 1], 0); }
+  for (int i = 0; i < n_lv; ++i)                                    // level 0 needs nothing from the pooling hierarchy: before it
+    if (lv[i].parent < 0) RUN(build_tables(i));
   // ---------------- pooled levels (sync-free: child counts stay on the device) ----------------
   int slot = 0;
   for (int i = 0; i < n_lv; ++i) {
@@ -184,35 +270,16 @@ CDSEG_API int cdseg_plan_build(const int32_t* grid, const int64_t* offset, int64
     }
     if (n_flags && flags_host) memcpy(flags_host, hf, (size_t)n_flags * 4);
   }
-  // ---------------- tables: neighbour indices, tap masks, conv tile plans, patch slot maps ----------------
-  int first0 = -1;
+  // ---------------- tables of the pooled levels + patch slot maps ----------------
+  if (two) { cudaEventRecord(g_pev[MAX_LV + 2], st); cudaStreamWaitEvent(sa, g_pev[MAX_LV + 2], 0); }     // the pooled grids come from `st`
+  defer = two;
   for (int i = 0; i < n_lv; ++i) {
     CdsegPlanLevel& L = lv[i];
-    if (L.parent < 0 && first0 >= 0) {                               // the second network's level 0: same points, same tables
-      const CdsegPlanLevel& F = lv[first0];
-      L.nbr3 = F.nbr3; L.tile_mask3 = F.tile_mask3; L.conv_plan3 = F.conv_plan3; L.nbr_stem = F.nbr_stem;
-    } else {
-      if (L.parent < 0) first0 = i;
-      const int64_t n = L.n;
-      L.nbr3 = (int32_t*)take((size_t)n * 27 * 4);
-      L.tile_mask3 = (uint32_t*)take(((size_t)n / 128 + 1) * 4);
-      L.conv_plan3 = nullptr;
-      L.nbr_stem = nullptr;
-      bool want_plan = L.want_conv_plan != 0, want_stem = L.stem_ksize > 0;
-      if (L.parent < 0)
-        for (int j = i + 1; j < n_lv; ++j)
-          if (lv[j].parent < 0) { want_plan |= lv[j].want_conv_plan != 0; want_stem |= lv[j].stem_ksize > 0; }
-      if (want_plan) L.conv_plan3 = take(cdseg_conv_plan_bytes(n));
-      const int sk = L.stem_ksize > 0 ? L.stem_ksize : 5;
-      if (want_stem) L.nbr_stem = (int32_t*)take((size_t)n * sk * sk * sk * 4);
-      if (oom) return CDSEG_ENOSPC;
-      if (n > 0) {
-        RUN(cdseg_nbr_build(L.grid, L.batch, n, 3, L.nbr3, ws, ws_bytes, st));
-        RUN(cdseg_tile_tap_mask(L.nbr3, n, 27, L.tile_mask3, st));
-        if (L.conv_plan3) RUN(cdseg_conv_tile_plan(L.nbr3, n, L.conv_plan3, st));
-        if (L.nbr_stem) RUN(cdseg_nbr_build(L.grid, L.batch, n, sk, L.nbr_stem, ws, ws_bytes, st));
-      }
-    }
+    if (L.parent >= 0) RUN(build_tables(i));
+    // patch maps: level 0 now (its blocks come first), pooled levels with the deferred launches -- on the aux stream then, so that
+    // `ready` orders them too
+    const bool later = defer && L.parent >= 0;
+    cudaStream_t sp = later ? sa : st;
     // patch maps, one per distinct PHYSICAL row among the wanted logical curves
     int64_t cnt[CDSEG_MAX_SCENES];
     for (int b = 0; b < B; ++b) cnt[b] = L.offset_host[b] - (b ? L.offset_host[b - 1] : 0);
@@ -237,7 +304,20 @@ CDSEG_API int cdseg_plan_build(const int32_t* grid, const int64_t* offset, int64
       for (int b = 0; b < B; ++b) pairs += cnt[b] * (cnt[b] > L.K ? L.K : cnt[b]);
       M.pairs = pairs;
       if (oom) return CDSEG_ENOSPC;
-      RUN(cdseg_patch_maps(L.order + (size_t)prow * N, cnt, B, L.K, Kp, M.slot_src, M.slot_dst, M.point_slot, M.patch_len, st));
+      if (later) {
+        const int32_t* ord = L.order + (size_t)prow * N;
+        const int K_ = L.K;
+        std::vector<int64_t> cv(cnt, cnt + B);
+        const CdsegPatchMap Mv = M;
+        cudaEvent_t ev = g_pev[i];
+        g_pending.push_back([ord, cv, B, K_, Kp, Mv, sp, ev]() -> int {
+          const int r = cdseg_patch_maps(ord, cv.data(), B, K_, Kp, Mv.slot_src, Mv.slot_dst, Mv.point_slot, Mv.patch_len, sp);
+          cudaEventRecord(ev, sp);                                   // re-record: `ready` now covers this map as well
+          return r;
+        });
+      } else {
+        RUN(cdseg_patch_maps(L.order + (size_t)prow * N, cnt, B, L.K, Kp, M.slot_src, M.slot_dst, M.point_slot, M.patch_len, sp));
+      }
     }
   }
 #undef RUN

@@ -19,6 +19,8 @@ __global__ void add_layernorm_kernel(const float* __restrict__ a, const float* _
                                      const float* __restrict__ t, const int32_t* __restrict__ batch,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                      int64_t n, int C, float* __restrict__ y_out, float* __restrict__ ln_out) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -62,7 +64,7 @@ CDSEG_API int cdseg_add_layernorm(const float* a, const float* b, const float* t
   if (C <= 0 || C > 1024 || (t && !batch) || (ln_out && (!gamma || !beta))) return CDSEG_EINVAL;
   if (n == 0) return CDSEG_OK;
   const int blocks = cdseg_div_up(n * 32, 256);
-#define LAUNCH_LN(V) add_layernorm_kernel<V><<<blocks, 256, 0, st>>>(a, b, t, batch, gamma, beta, eps, n, C, y_out, ln_out)
+#define LAUNCH_LN(V) cdseg_launch_pdl(add_layernorm_kernel<V>, dim3(blocks), dim3(256), 0, st, a, b, t, batch, gamma, beta, eps, n, C, y_out, ln_out)
   if (C <= 32) LAUNCH_LN(1);
   else if (C <= 64) LAUNCH_LN(2);
   else if (C <= 128) LAUNCH_LN(4);
@@ -143,6 +145,8 @@ __global__ void reduce_ln4_kernel(const float* __restrict__ part, int nsplit, co
                                   const float* __restrict__ b1, const float* __restrict__ res, const float* __restrict__ t,
                                   const int32_t* __restrict__ batch, const float* __restrict__ g2, const float* __restrict__ b2, float eps,
                                   int64_t n, int C, float* __restrict__ y_out, float* __restrict__ ln_out) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -210,7 +214,7 @@ CDSEG_API int cdseg_reduce_ln(const float* part, int nsplit, const float* bias, 
                         (uintptr_t)b2 | (uintptr_t)y_out | (uintptr_t)ln_out) & 15);
   if ((C == 128 || C == 256 || C == 512) && al16) {            // 4 rows per CTA: 990 rows still give 248 CTAs
     const int blocks4 = cdseg_div_up(n * 32, 128);
-#define LAUNCH_RL4(G) reduce_ln4_kernel<G><<<blocks4, 128, 0, st>>>(part, nsplit, bias, g1, b1, res, t, batch, g2, b2, eps, n, C, y_out, ln_out)
+#define LAUNCH_RL4(G) cdseg_launch_pdl(reduce_ln4_kernel<G>, dim3(blocks4), dim3(128), 0, st, part, nsplit, bias, g1, b1, res, t, batch, g2, b2, eps, n, C, y_out, ln_out)
     if (C == 128) LAUNCH_RL4(1);
     else if (C == 256) LAUNCH_RL4(2);
     else LAUNCH_RL4(4);

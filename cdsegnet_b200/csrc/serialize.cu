@@ -11,12 +11,16 @@
 // All kernels are HBM/L2-bound integer work: coalesced 32/64-bit accesses, one
 // thread per element, keys staged through shared memory in the sort.
 #include "common.cuh"
+#include <cstdlib>
 
 unsigned long long g_cdseg_launches = 0;
+int g_cdseg_pdl = [] { const char* e = getenv("CDSEG_PDL"); return e ? atoi(e) : 1; }();        // common.cuh: programmatic dependent launch
+CDSEG_API void cdseg_set_pdl(int on) { g_cdseg_pdl = on; }
+CDSEG_API int cdseg_get_pdl(void) { return g_cdseg_pdl; }
 
 CDSEG_API unsigned long long cdseg_launch_count(void) { return g_cdseg_launches; }
 CDSEG_API void cdseg_launch_count_reset(void) { g_cdseg_launches = 0; }
-CDSEG_API int cdseg_abi_version(void) { return 2; }
+CDSEG_API int cdseg_abi_version(void) { return 3; }
 
 // ---------------------------------------------------------------------------------
 // grid max (for serialized_depth = bit_length(max), structure.py:66)

@@ -222,11 +222,11 @@ def _arena(key, nbytes, device):
     return a
 
 
-def forward_native(model, plan, n_feat, c_feat, t_emb, mode, main, side):
+def forward_native(model, plan, n_feat, c_feat, t_emb, mode, main, side, nw=None, outs=None):
     """feature phase of one forward through cdseg_net_forward.  n_feat / c_feat: fp32 [N, cin] in the caller's numbering; t_emb: fp32
     [B, T_dim] (one row per scene) or None.  Returns (n_out, c_out) in the caller's numbering."""
     lib = _lib.load()
-    nw = weights(model)
+    nw = nw if nw is not None else weights(model)
     dev = n_feat.device
     N, B = n_feat.shape[0], plan.n_levels[0].B
     a = ForwardArgs()
@@ -234,11 +234,13 @@ def forward_native(model, plan, n_feat, c_feat, t_emb, mode, main, side):
     a.levels = ctypes.cast(plan.desc, ctypes.POINTER(PlanLevel))
     a.n_lv_n, a.n_lv_c = len(plan.n_levels), len(plan.c_levels) if plan.c_levels else 0
     a.N, a.B, a.attn_mode = N, B, ops.ATTN_MODES.index(mode)
-    n_out = torch.empty((N, nw.w.n_head.N), dtype=torch.float32, device=dev)
+    n_out, c_out = outs if outs is not None else (None, None)
+    if n_out is None:
+        n_out = torch.empty((N, nw.w.n_head.N), dtype=torch.float32, device=dev)
     a.n_feat, a.n_out = _f32(n_feat), n_out.data_ptr()
-    c_out = None
     if model.condition:
-        c_out = torch.empty((N, nw.w.c_head.N), dtype=torch.float32, device=dev)
+        if c_out is None:
+            c_out = torch.empty((N, nw.w.c_head.N), dtype=torch.float32, device=dev)
         a.c_feat, a.c_out = _f32(c_feat), c_out.data_ptr()
         a.t_emb = _f32(t_emb)
     a.stream_main = main.cuda_stream
@@ -255,6 +257,11 @@ def forward_native(model, plan, n_feat, c_feat, t_emb, mode, main, side):
         for t in (c_feat, t_emb, c_out):
             if t is not None:
                 t.record_stream(side)
+    if main.cuda_stream != torch.cuda.current_stream(dev).cuda_stream:       # the caller forked `main` off its own stream (ptv3.py priority streams)
+        plan.arena.record_stream(main)
+        for t in (n_feat, c_feat, t_emb, n_out, c_out):
+            if t is not None:
+                t.record_stream(main)
     evs = None
     if ops.PROFILE is not None:                          # bench.py: CUDA events around the pre / attention / post kernels of every block
         nb = len(nw.blocks)

@@ -14,6 +14,7 @@ Inference-only in this round (SSI forward, default.py:371-422); autograd through
 custom kernels is the next §8(f) row.
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -536,6 +537,8 @@ class PointTransformerV3(nn.Module):
         # the bug this schedule exposed at full overlap: a missing generic->async proxy fence in the fused kernels' input rings,
         # profiles/r02_two_stream_race.md.)
         self.overlap_streams = True
+        self.priority_streams = os.environ.get("CDSEG_PRIORITY_STREAMS", "1") != "0"
+        self.plan_aux_stream = os.environ.get("CDSEG_PLAN_AUX", "1") != "0"
         self.perm_fn = None                  # tests / bench: replaces the CPU torch.randperm draws of shuffle_orders (structure.py:95, ptv3.py:502)
         self.n_cfg = dict(stride=n_stride, enc_depths=n_enc_depths, dec_depths=n_dec_depths)
         self.c_cfg = dict(stride=c_stride, enc_depths=c_enc_depths, dec_depths=c_dec_depths)
@@ -644,8 +647,26 @@ class PointTransformerV3(nn.Module):
         dev = (n_point if n_point is not None else c_point)["coord"].device
         if dev.type != "cuda":
             raise RuntimeError("cdsegnet_b200: inputs must be CUDA tensors (no CPU fallback)")
-        with ops.stream_scope(torch.cuda.current_stream(dev)):
-            return self._forward(c_point, n_point, perm_fn or self.perm_fn)
+        cur = torch.cuda.current_stream(dev)
+        run = cur
+        if self.priority_streams and self.overlap_streams and self.condition and ops.NATIVE_NET:
+            # The 5-stage network (and the plan's pooling chain before it) is the critical path: 8.6 ms of kernels against the 3-stage
+            # network's 3.5 ms (profiles/r02_timeline.md).  On equal priorities its small kernels queue behind every wide grid of the
+            # other streams, so the whole forward is forked onto a high-priority stream (pending CTAs of a higher priority are dispatched
+            # first); the 3-stage network and the plan's table builder run at the lowest priority, which is also the default stream's.
+            run = self._side_stream(cur, "main")
+            run.wait_stream(cur)
+        with ops.stream_scope(run):
+            out = self._forward(c_point, n_point, perm_fn or self.perm_fn)
+        if run is not cur:
+            cur.wait_stream(run)
+            for p in (out if isinstance(out, tuple) else (out,)):
+                for v in p.values():
+                    if torch.is_tensor(v) and v.is_cuda:
+                        v.record_stream(cur)
+            if getattr(self, "last_plan", None) is not None:
+                self.last_plan.arena.record_stream(cur)      # exported Points hold lazy views into it
+        return out
 
     def _forward(self, c_point, n_point, perm_fn):
         exact = self.attention_mode                  # one of ops.ATTN_MODES, handed down to every attention layer
@@ -661,11 +682,18 @@ class PointTransformerV3(nn.Module):
         if flags is not None and t_emb.shape[0] != offset.numel():
             ops.rows_uniform_flag(t_emb, ops.offset2batch(offset.long().contiguous(), t_emb.shape[0]),
                                   offset.long().contiguous(), flags)
+        aux = None
+        if self.plan_aux_stream and ops.NATIVE_NET and grid.is_cuda:
+            # the indice tables are built on a third stream beside the pooling hierarchy and the first kernels of the forward;
+            # cdseg_net_forward waits on the per-level events (profiles/r02_timeline.md: the plan phase was 1.07 ms, serial)
+            aux = self._side_stream(torch.cuda.current_stream(), "aux")
+        pre = self._native_prepare(c_point, n_point, t_emb, exact) if ops.NATIVE_NET else None
         plan = Plan(grid, offset, self.order, self.n_cfg["stride"], self.c_cfg["stride"] if self.condition else None,
-                    self.shuffle_orders, perm_fn, flags, spec=self.plan_spec)
+                    self.shuffle_orders, perm_fn, flags, spec=self.plan_spec, aux=aux)
         self.last_plan = plan
         nl = plan.n_levels
-        native = self._forward_native(plan, c_point, n_point, t_emb, exact)
+        native = self._forward_native(plan, pre, c_point, n_point, exact)
+        plan.join_aux()              # after a native forward: already complete on the device (the forward waited for every level), free
         if native is not None:
             return native
         n = self._prep(n_point, nl[0])
@@ -733,31 +761,48 @@ class PointTransformerV3(nn.Module):
             main.wait_stream(side)
         return self._export(c), self._export(n)
 
-    def _forward_native(self, plan, c_point, n_point, t_emb, mode):
-        """the whole feature phase through cdseg_net_forward (csrc/net_exec.cu); None when this forward needs the per-module path
-        (per-point timestep rows that differ inside a scene, ops.NATIVE_NET off, comparator GEMM / attention kernels selected)"""
+    def _native_prepare(self, c_point, n_point, t_emb, mode):
+        """everything of the native feature phase that does not need the plan, done BEFORE the plan is built: after the plan's second
+        host sync the GPU is waiting for the host, so whatever runs between that sync and the first launch of cdseg_net_forward is on the
+        critical path (profiles/r02_timeline.md).  None when this forward needs the per-module path."""
         from . import netexec
         if not netexec.supported(self) or (mode == "f16" and ops.ATTN_KERNEL != 3):
             return None
-        ts = None
-        offset = n_point["offset"]
-        B = offset.numel()
-        if self.condition and t_emb is not None:
-            if self.t_emb_per_scene and t_emb.shape[0] == B and B != n_point["feat"].shape[0]:
-                ts = t_emb                                              # already one row per scene
-            elif self.t_emb_per_scene and plan.flags is not None and int(plan.flags[0]) == 0:
-                first = torch.cat([offset.new_zeros(1), offset[:-1]]).long()
-                ts = t_emb.index_select(0, first).contiguous()           # rows are identical inside a scene
-            else:
-                return None
         for d in (n_point, c_point):
             if d is not None and not (d["feat"].is_cuda and d["coord"].is_cuda):
                 raise RuntimeError("cdsegnet_b200: inputs must be CUDA tensors (no CPU fallback)")
-        main = torch.cuda.current_stream()
-        side = self._side_stream(main) if (self.overlap_streams and self.condition) else None
+        ts, need_flag = None, False
+        offset = n_point["offset"]
+        B = offset.numel()
+        if self.condition and t_emb is not None:
+            if not self.t_emb_per_scene:
+                return None
+            if t_emb.shape[0] == B and B != n_point["feat"].shape[0]:
+                ts = t_emb                                              # already one row per scene
+            else:                                                       # valid if the rows are identical inside a scene (plan.flags)
+                first = torch.cat([offset.new_zeros(1), offset[:-1]]).long()
+                ts = t_emb.index_select(0, first).contiguous()
+                need_flag = True
+        nw = netexec.weights(self)
         n_feat = n_point["feat"].float().contiguous()
         c_feat = c_point["feat"].float().contiguous() if self.condition else None
-        n_out, c_out = netexec.forward_native(self, plan, n_feat, c_feat, ts, mode, main, side)
+        N, dev = n_feat.shape[0], n_feat.device
+        n_out = torch.empty((N, nw.w.n_head.N), dtype=torch.float32, device=dev)
+        c_out = torch.empty((N, nw.w.c_head.N), dtype=torch.float32, device=dev) if self.condition else None
+        return dict(ts=ts, need_flag=need_flag, nw=nw, n_feat=n_feat, c_feat=c_feat, n_out=n_out, c_out=c_out)
+
+    def _forward_native(self, plan, pre, c_point, n_point, mode):
+        """the whole feature phase through cdseg_net_forward (csrc/net_exec.cu); None when this forward needs the per-module path
+        (per-point timestep rows that differ inside a scene, ops.NATIVE_NET off, comparator GEMM / attention kernels selected)"""
+        from . import netexec
+        if pre is None:
+            return None
+        if pre["need_flag"] and (plan.flags is None or int(plan.flags[0]) != 0):
+            return None
+        main = torch.cuda.current_stream()
+        side = self._side_stream(main) if (self.overlap_streams and self.condition) else None
+        n_out, c_out = netexec.forward_native(self, plan, pre["n_feat"], pre["c_feat"], pre["ts"], mode, main, side, nw=pre["nw"],
+                                              outs=(pre["n_out"], pre["c_out"]))
 
         def export(d, feat, level):
             p = Point(d)
@@ -773,11 +818,14 @@ class PointTransformerV3(nn.Module):
             return n
         return export(c_point, c_out, plan.c_levels[0]), n
 
-    def _side_stream(self, main):
-        key = main.device
-        if getattr(self, "_side", None) is None or self._side[0] != key:
-            self._side = (key, torch.cuda.Stream(device=main.device))
-        return self._side[1]
+    def _side_stream(self, main, kind="side"):
+        """cached streams per device: "main" (high priority: the plan's pooling chain and the 5-stage network), "side" / "aux" (lowest
+        priority: the 3-stage network, the plan's table builder)"""
+        key = (main.device, kind)
+        cache = self.__dict__.setdefault("_streams", {})
+        if key not in cache:
+            cache[key] = torch.cuda.Stream(device=main.device, priority=-1 if kind == "main" else 0)      # 0 = lowest = default
+        return cache[key]
 
     @staticmethod
     def _export(p):

@@ -207,7 +207,7 @@ class Plan:
     (direct users, tests) they are built on first use."""
 
     def __init__(self, grid_coord, offset, orders, n_strides, c_strides=None, shuffle_orders=True, perm_fn=None,
-                 extra_flags=None, spec=None):
+                 extra_flags=None, spec=None, aux=None):
         perm_fn = perm_fn or torch_randperm
         dev = grid_coord.device
         if dev.type != "cuda":
@@ -269,7 +269,12 @@ class Plan:
         fh = (ctypes.c_int32 * max(n_flags, 1))()
         check(lib.cdseg_plan_build(grid.data_ptr(), offset.data_ptr(), N, B, ids, k, d, n_lv,
                                    extra_flags.data_ptr() if n_flags else None, n_flags, fh, self._base, self.arena.numel(),
-                                   ops._stream()), "plan_build")
+                                   ops._stream(), aux.cuda_stream if aux is not None else None), "plan_build")
+        # aux (a torch.cuda.Stream): the indice tables are built there and only the per-level `ready` events order them (cdseg_net_forward
+        # waits on those); any other reader calls join_aux() first
+        self.aux = aux
+        if aux is not None:
+            self.arena.record_stream(aux)
         self.flags = np.array([fh[i] for i in range(n_flags)], dtype=np.int64) if n_flags else None
         self.n_levels = [Level(self, index[("n", s)], k) for s in range(n_n)]
         self.c_levels = [Level(self, index[("c", s)], k) for s in range(n_c)] if n_c else None
@@ -278,6 +283,13 @@ class Plan:
                 levels[s].parent = levels[s - 1]
         if self.c_levels:
             self.n_levels[0]._nbr = self.c_levels[0]._nbr          # same points, same numbering: share lazily built tables too
+
+    def join_aux(self):
+        """make the current stream wait for the tables built on the aux stream (no-op without one)"""
+        if self.aux is not None:
+            check(_lib.load().cdseg_plan_finish(), "plan_finish")      # launches an aux-stream build leaves for later (no-op after a native forward)
+            torch.cuda.current_stream().wait_stream(self.aux)
+            self.aux = None
 
     def view(self, ptr, shape, dtype):
         """tensor view of arena memory (or of the caller's offset tensor) at raw device pointer `ptr`"""

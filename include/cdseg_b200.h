@@ -20,6 +20,10 @@ extern "C" {
 #endif
 
 int cdseg_abi_version(void);
+/* programmatic dependent launch between consecutive kernels of a stream (on by default; CDSEG_PDL=0 in the environment or 0 here
+ * turns it off: every launch then waits for the full completion of its predecessor before its first CTA is scheduled) */
+void cdseg_set_pdl(int on);
+int cdseg_get_pdl(void);
 /* number of kernels launched through this library since the last reset (bench.py "gpu_launches") */
 unsigned long long cdseg_launch_count(void);
 void cdseg_launch_count_reset(void);
@@ -204,6 +208,8 @@ int cdseg_conv_tile_plan(const int32_t* nbr, int64_t n, void* plan, void* stream
 /* which fused kernels cdseg_block_forward uses: bit 0 post-attention chain, bit 1 pre-attention chain, bit 2 split-K reduction fused with
  * the LayerNorms that follow it at the wide levels (default: all) */
 void cdseg_set_fused_mask(int mask);
+/* resident CTAs per SM of the persistent fused kernels launched from now on (0 = as many as fit, the default) */
+void cdseg_set_fused_ctas_per_sm(int n);
 
 /* ---- native plan phase (plan_exec.cu): serialization + pooling hierarchy + indice tables + patch maps of BOTH networks in one call --
  * Replaces Point.serialization (structure.py:47-102), the structural half of every SerializedPooling (ptv3.py:464-505), the spconv
@@ -229,11 +235,20 @@ typedef struct CdsegPlanLevel {
   int32_t* perm; int32_t* inv_perm; int64_t* o_code; int32_t* o_order; int32_t* o_inverse; /* level 0: internal <-> caller numbering, originals */
   int32_t* nbr3; uint32_t* tile_mask3; void* conv_plan3; int32_t* nbr_stem;
   CdsegPatchMap pm[4];                /* by LOGICAL curve index */
+  /* out: NULL, or (plan built with an aux stream) the cudaEvent_t after which nbr3 / tile_mask3 / conv_plan3 (`ready`) and nbr_stem
+   * (`ready_stem`) of this level are complete; a consumer makes its stream wait on them before the first kernel that reads those tables.
+   * Everything else in the descriptor is ordered by `stream` itself. */
+  void* ready; void* ready_stem;
 } CdsegPlanLevel;
 size_t cdseg_plan_arena_bytes(int64_t N, int B, int k, int n_levels, int n_level0, int stem_ksize, int K_min, int K_max);
 int cdseg_plan_build(const int32_t* grid, const int64_t* offset, int64_t N, int B, const int* order_ids, int k,
                      CdsegPlanLevel* levels, int n_levels, const int32_t* extra_flags, int n_flags, int32_t* flags_host,
-                     void* arena, size_t arena_bytes, void* stream);
+                     void* arena, size_t arena_bytes, void* stream, void* aux_stream /* NULL: everything on `stream` */);
+/* With an aux stream the launches that build the pooled levels' tables and slot maps are NOT enqueued by cdseg_plan_build (the
+ * descriptors are complete, the device data is not): cdseg_plan_finish() enqueues them on the aux stream and records the `ready`
+ * events.  cdseg_net_forward calls it itself before its first pooled stage; any other consumer calls it before waiting on `ready`.
+ * Idempotent; one plan at a time per process. */
+int cdseg_plan_finish(void);
 
 /* ---- native executor of one PTv3 Block (ptv3.py:399-428): the 12-13 launches above enqueued from C++ in one call --- */
 #define CDSEG_ATTN_F16 0

@@ -62,3 +62,29 @@ structure.Plan.__init__ = origP
 import cProfile, pstats, io
 pr = cProfile.Profile(); pr.enable(); seg.inference(res, eval=False, noise=noise); torch.cuda.synchronize(); pr.disable()
 s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22); print(s.getvalue()[:5000])
+
+# 4) host timeline of one forward: when each C-ABI call starts / returns, relative to the start of seg.inference
+from cdsegnet_b200 import _lib
+lib = _lib.load()
+marks = []
+def wrap(name):
+    fn = getattr(lib, name)
+    def w(*a):
+        t0 = time.perf_counter(); r = fn(*a); marks.append((name, t0, time.perf_counter())); return r
+    setattr(lib, name, w)
+for nm in ("cdseg_plan_build", "cdseg_net_arena_bytes", "cdseg_net_forward"):
+    wrap(nm)
+rows = []
+for _ in range(6):
+    torch.cuda.synchronize()
+    marks.clear()
+    t0 = time.perf_counter()
+    seg.inference(res, eval=False, noise=noise)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    rows.append([(n, 1e6 * (a - t0), 1e6 * (b - t0)) for n, a, b in marks] + [("inference returns", 1e6 * (t1 - t0), 1e6 * (t2 - t0))])
+med = rows[-1]
+print("host timeline of the last forward (us from the start of seg.inference): call, enter, return")
+for n, a, b in med:
+    print(f"  {n:24s} {a:9.1f} {b:9.1f}")

@@ -123,7 +123,7 @@ def test_cabi_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.cdseg_abi_version() == 2
+    assert lib.cdseg_abi_version() == 3
 
 
 @pytest.mark.parametrize("depth", DEPTHS)
