@@ -104,6 +104,7 @@ struct Params {
   float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
   int nw;                                 // output-tile width in columns (32 / 64 / 128): a CTA owns columns [blockIdx.y * nw, + nw)
   int vec_ok;                             // output / residual rows are 16-byte aligned
+  int a256;                               // A rows are 32-byte aligned: 256-bit loads (half the LSU wavefronts of the row gather)
   int AT, SB, b_bytes, acc_cols, tmem_cols;   // A ring slots (TMEM), B ring stages (smem), bytes of one B block, TMEM layout
   long long* trace; int trace_cta;        // profiling hook: clock64 stamps of one CTA (null in production)
   int single;                             // 1: fp16 x fp16 products only (hi.hi; the lo terms are skipped): the reduced-precision mode
@@ -117,6 +118,15 @@ struct Bars {
   uint32_t tmem_slot, pad;
   uint8_t taps[32];                       // present taps of this CTA's split, ascending
 };
+
+// 256-bit read-only global load (sm_100: LDG.256).  The A gather has every lane of a warp on a different row, so each warp-level load
+// costs one L1 wavefront per lane whatever its width: 32-byte loads halve the wavefronts per k-chunk, which is what bounds the deep
+// levels' launches (profiles/r02_trace_gemm_deep.txt: 1 200 - 1 800 cycles per k-iteration with four producer warps per SM).
+__device__ __forceinline__ void ldg256(const float* ptr, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(ptr));
+}
 
 // D[tmem] (+)= A[tmem] . B[smem]   (A: lane = row, two fp16 K elements per 32-bit column)
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -155,14 +165,9 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
   const int t_begin = (int)((long long)p.T * z / p.nsplit), t_end = (int)((long long)p.T * (z + 1) / p.nsplit);
 
   PDL_TRIGGER_EARLY();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < MAX_RING; ++s) {
-      mbar_init(smem_u32(&bars->full_a[s]), 128);
-      mbar_init(smem_u32(&bars->empty_a[s]), 1);
-      mbar_init(smem_u32(&bars->full_b[s]), 1);
-      mbar_init(smem_u32(&bars->empty_b[s]), 1);
-    }
-    mbar_init(smem_u32(&bars->acc), 1);
+  if (threadIdx.x < 4 * MAX_RING + 1) {              // one barrier per thread (Bars: full_a, empty_a, full_b, empty_b, acc are contiguous)
+    const int b = threadIdx.x;
+    mbar_init(smem_u32(&bars->full_a[0]) + 8u * b, b < MAX_RING ? 128u : 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
@@ -221,7 +226,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
           const int s8 = (row_ok && tap < p.taps_ld) ? __ldg(p.idx + m * p.taps_ld + tap) : -1;
           if (s8 >= 0) {
             const float4* row = reinterpret_cast<const float4*>(p.A + (long long)s8 * 8);
-            v[2 * q] = __ldg(row); v[2 * q + 1] = __ldg(row + 1);
+            if (p.a256) ldg256(p.A + (long long)s8 * 8, v[2 * q], v[2 * q + 1]);
+            else { v[2 * q] = __ldg(row); v[2 * q + 1] = __ldg(row + 1); }
           } else {
             v[2 * q] = v[2 * q + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -234,8 +240,16 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
       const int kleft = p.K - kc * KC;                                  // valid fp32 elements of this chunk (K may be 16 mod 32)
       if (src >= 0) {
         const float4* row = reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) + kc * (KC / 4);
+        if (p.a256) {
 #pragma unroll
-        for (int j = 0; j < KC / 4; ++j) v[j] = j * 4 < kleft ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < KC / 4; j += 2) {
+            if (j * 4 < kleft) ldg256(reinterpret_cast<const float*>(row + j), v[j], v[j + 1]);   // kleft is a multiple of 8 here
+            else v[j] = v[j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < KC / 4; ++j) v[j] = j * 4 < kleft ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < KC / 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -429,6 +443,30 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int nsplit,
   if (act == 1) s = gelu_erf(s);
   if (res) s += res[m * ldr + n];
   out[m * ldo + n] = s;
+}
+
+// the same for N % 4 == 0 and 16-byte aligned rows: four columns per thread (the partials are summed in the same order z = 0, 1, ...
+// per element, so the result is bit-identical to the scalar kernel's)
+__global__ void splitk_reduce4_kernel(const float4* __restrict__ part, int nsplit, long long M, int N4,
+                                      const float4* __restrict__ bias, const float* __restrict__ res, long long ldr,
+                                      int act, float* __restrict__ out, long long ldo) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long MN4 = M * N4;
+  if (i >= MN4) return;
+  const long long m = i / N4;
+  const int n4 = (int)(i % N4);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int z = 0; z < nsplit; ++z) {
+    const float4 v = part[(long long)z * MN4 + i];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  if (bias) { const float4 b = __ldg(bias + n4); s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w; }
+  if (act == 1) { s.x = gelu_erf(s.x); s.y = gelu_erf(s.y); s.z = gelu_erf(s.z); s.w = gelu_erf(s.w); }
+  if (res) { const float4 r = *reinterpret_cast<const float4*>(res + m * ldr + 4 * n4); s.x += r.x; s.y += r.y; s.z += r.z; s.w += r.w; }
+  *reinterpret_cast<float4*>(out + m * ldo + 4 * n4) = s;
 }
 
 // per 128-row tile: OR over rows of (nbr[row][t] >= 0) << t     (T <= 32)
@@ -650,6 +688,8 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   p.AT = AT; p.SB = SB; p.b_bytes = b_bytes; p.acc_cols = acc_cols; p.tmem_cols = tmem_cols;
   p.trace = g_trace; p.trace_cta = g_trace_cta;
   p.single = g_cdseg_gemm_single;
+  static const bool no256 = [] { const char* e = getenv("CDSEG_NO_LDG256"); return e && atoi(e) != 0; }();
+  p.a256 = (!no256 && ((uintptr_t)A & 31) == 0 && (lda & 7) == 0 && (K & 7) == 0) ? 1 : 0;
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + nw - 1) / nw, nsplit);
@@ -657,8 +697,14 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   else cdseg_launch_pdl(gt::gemm_tc_kernel<2>, g, dim3(gt::NTHREADS), smem, st, p);
   CDSEG_COUNT_LAUNCH(1);
   if (nsplit > 1 && out) {                   // out == NULL: the caller consumes the raw partials part[z][M][N] itself (cdseg_reduce_ln)
-    cdseg_launch_pdl(gt::splitk_reduce_kernel, dim3(cdseg_div_up(M * N, 256)), dim3(256), 0, st, (const float*)workspace, nsplit,
-                     (long long)M, N, bias, res, (long long)ldr, act, out, (long long)ldo);
+    const bool v4 = (N & 3) == 0 && (ldo & 3) == 0 && (!res || (ldr & 3) == 0) &&
+                    !(((uintptr_t)workspace | (uintptr_t)bias | (uintptr_t)res | (uintptr_t)out) & 15);
+    if (v4)
+      cdseg_launch_pdl(gt::splitk_reduce4_kernel, dim3(cdseg_div_up(M * (N / 4), 256)), dim3(256), 0, st, (const float4*)workspace, nsplit,
+                       (long long)M, N / 4, (const float4*)bias, res, (long long)ldr, act, out, (long long)ldo);
+    else
+      cdseg_launch_pdl(gt::splitk_reduce_kernel, dim3(cdseg_div_up(M * N, 256)), dim3(256), 0, st, (const float*)workspace, nsplit,
+                       (long long)M, N, bias, res, (long long)ldr, act, out, (long long)ldo);
     CDSEG_COUNT_LAUNCH(1);
   }
   CDSEG_LAUNCH_CHECK();
