@@ -104,6 +104,7 @@ struct Params {
   float* part; int nsplit;                // nsplit > 1: raw partial sums to part[z][M][N]
   int nw;                                 // output-tile width in columns (32 / 64 / 128): a CTA owns columns [blockIdx.y * nw, + nw)
   int vec_ok;                             // output / residual rows are 16-byte aligned
+  int fast_epi;                           // aligned full-width tiles: the compact epilogue (see the kernel)
   int a256;                               // A rows are 32-byte aligned: 256-bit loads (half the LSU wavefronts of the row gather)
   int AT, SB, b_bytes, acc_cols, tmem_cols;   // A ring slots (TMEM), B ring stages (smem), bytes of one B block, TMEM layout
   long long* trace; int trace_cta;        // profiling hook: clock64 stamps of one CTA (null in production)
@@ -303,6 +304,54 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
     const bool final_out = p.nsplit == 1;
     float* obase = final_out ? p.out : p.part + (long long)z * p.M * p.N;
     const long long old = final_out ? p.ldo : (long long)p.N;
+    if (p.fast_epi && (wn & 31) == 0 && n_iter > 0) {
+      // Compact epilogue for the common case (aligned rows, tile width a multiple of 32, so every pass is 32 full columns).  The general
+      // loop below compiles to ~2 300 instructions per pass (scalar fallbacks, 64-bit index arithmetic per element); with one producer
+      // warp per scheduler at the deep levels that is 2 500 cycles per pass and 10 000 per 128-column tile
+      // (profiles/r02_trace_gemm_deep.txt).  Same arithmetic in the same order: bit-identical results.
+      const int rsub = lane >> 3, cc = (lane & 7) * 4;
+      const long long m0 = (long long)tile_m * BM + warp * 32 + rsub;
+      const long long left = (long long)p.M - m0;
+      const int nvalid = left <= 0 ? 0 : (left >= 29 ? 8 : (int)((left + 3) >> 2));      // rows m0 + 4 i < M
+      const bool has_res = final_out && p.res != nullptr;
+      const bool do_gelu = final_out && p.act == 1;
+      const bool has_bias = final_out && p.bias != nullptr;
+      float* op0 = obase + m0 * old + n0 + cc;
+      const float* rp0 = has_res ? p.res + m0 * p.ldr + n0 + cc : nullptr;
+      const long long ostep = 4 * old, rstep = 4 * p.ldr;
+      const float* srow = stg + rsub * SLD + cc;
+      for (int c0 = 0; c0 < wn; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld16(tmem + lane_base + c0, acc);
+        tmem_ld16(tmem + lane_base + c0 + 16, acc + 16);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + cc));
+        float4 q[8];
+        if (has_res) {
+          const float* rp = rp0 + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i, rp += rstep) q[i] = i < nvalid ? __ldg(reinterpret_cast<const float4*>(rp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<uint4*>(stg + lane * SLD + j4 * 4) = make_uint4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
+        __syncwarp();
+        float* op = op0 + c0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i, op += ostep) {
+          if (i < nvalid) {
+            float4 v = *reinterpret_cast<const float4*>(srow + i * 4 * SLD);
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (do_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+            if (has_res) { v.x += q[i].x; v.y += q[i].y; v.z += q[i].z; v.w += q[i].w; }
+            *reinterpret_cast<float4*>(op) = v;
+          }
+        }
+        __syncwarp();
+        if (tr && threadIdx.x == 0 && c0 / 32 < 4) p.trace[6 + c0 / 32] = clock64();   // epilogue pass done
+      }
+    } else
     for (int c0 = 0; c0 < un; c0 += 32) {
       const int cw = min(32, un - c0);              // 32 or 16 accumulator columns in this pass
       uint32_t acc[32];
@@ -690,8 +739,11 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   p.single = g_cdseg_gemm_single;
   static const bool no256 = [] { const char* e = getenv("CDSEG_NO_LDG256"); return e && atoi(e) != 0; }();
   p.a256 = (!no256 && ((uintptr_t)A & 31) == 0 && (lda & 7) == 0 && (K & 7) == 0) ? 1 : 0;
+  static const bool no_fast = [] { const char* e = getenv("CDSEG_NO_FAST_EPI"); return e && atoi(e) != 0; }();
+  p.fast_epi = 0;                                  // set below, once vec_ok is known
   p.vec_ok = ((ldo & 3) == 0 && (!res || (ldr & 3) == 0) && (N & 3) == 0 && ((uintptr_t)out & 15) == 0 &&
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
+  p.fast_epi = (!no_fast && p.vec_ok && (nw & 31) == 0 && !(((uintptr_t)bias | (uintptr_t)workspace) & 15)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + nw - 1) / nw, nsplit);
   if (dense3) cdseg_launch_pdl(gt::gemm_tc_kernel<3>, g, dim3(gt::NTHREADS), smem, st, p);
   else cdseg_launch_pdl(gt::gemm_tc_kernel<2>, g, dim3(gt::NTHREADS), smem, st, p);
