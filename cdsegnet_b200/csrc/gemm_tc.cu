@@ -149,7 +149,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // into fp16 hi / lo and stores both straight into TENSOR MEMORY (lane == row), from where tcgen05.mma reads it (TS form).
 // Variants measured on B200 for the stage-0 conv (120k x 27 taps x 32->32), see profiles/r01_gemm_tc_history.md:
 // smem-A tf32 143 us, +deep cp.async ring 270 us, TMEM-A tf32 152 us, TMEM-A fp16 (this) 127 us, coalesced smem-A 230 us.
-template <int MINB>
+template <int MINB, int AMODE>
 __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int AT = p.AT, SB = p.SB, B_BYTES = p.b_bytes;
@@ -201,25 +201,34 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
   // -> iteration it = (tap taps[it / kch], chunk it % kch)
   const int n_iter = ntap * kch;
   auto tap_of = [&](int it) { const int j = it / kch; return p.T <= 32 ? (int)bars->taps[j] : t_begin + j; };
+  auto tap_of_slot = [&](int j) { return p.T <= 32 ? (int)bars->taps[j] : t_begin + j; };
 
   if (warp < 4) {
     // ------------------------------- A producers -------------------------------
+    // AMODE (compile time, so that each launch runs only its own address arithmetic -- the generic version of this loop was ~480
+    // instructions per k-iteration, and with one producer warp per scheduler at the deep levels that IS the iteration time):
+    //   0 dense rows (Linear, split-K slices)   1 gathered rows, tile's indices staged in shared memory (T <= 32)
+    //   2 im2col (4 taps x 8 channels per chunk)   3 gathered rows, indices read from global memory (T > 32)
     const int r = threadIdx.x;
     const long long m = (long long)tile_m * BM + r;
     const bool row_ok = m < p.M;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    // this tile's neighbour indices, staged once in shared memory (one coalesced block read) so that the per-tap
-    // row address no longer hangs off a dependent global load
     int32_t* s_idx = reinterpret_cast<int32_t*>(s_b + (size_t)SB * 2 * B_BYTES + sizeof(Bars) + 64);
-    const bool idx_smem = p.idx != nullptr && p.T <= 32 && !p.sub;
-    if (idx_smem) {
+    if (AMODE == 1) {
+      // this tile's neighbour indices, staged once (one coalesced block read) so that the per-tap row address no longer hangs off a
+      // dependent global load
       const long long base = (long long)tile_m * BM * p.T, total = (long long)p.M * p.T;
       for (int j = r; j < BM * p.T; j += 128) s_idx[j] = base + j < total ? __ldg(p.idx + base + j) : -1;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    auto fetch = [&](int it, float4* v) {
-      const int t = tap_of(it), kc = it - (it / kch) * kch;
-      if (p.sub) {
+    const bool full_k = (p.K % KC) == 0;
+    // fetches are requested in iteration order: (tap slot fj, chunk fkc) advance incrementally instead of it / kch, it % kch
+    int fj = 0, fkc = 0;
+    auto fetch = [&](float4* v) {
+      const int t = AMODE == 0 ? t_begin + fj : tap_of_slot(fj);
+      const int kc = fkc;
+      if (++fkc == kch) { fkc = 0; ++fj; }
+      if (AMODE == 2) {
         // im2col chunk (tiny C_in, padded to 8): K = 32 = 4 taps x 8 channels, each tap a 32-byte row of A
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -236,18 +245,18 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
         return;
       }
       long long src = -1;
-      if (idx_smem) src = s_idx[r * p.T + t];
-      else if (row_ok) src = p.idx ? (long long)__ldg(p.idx + m * p.T + t) : m;
-      const int kleft = p.K - kc * KC;                                  // valid fp32 elements of this chunk (K may be 16 mod 32)
+      if (AMODE == 1) src = s_idx[r * p.T + t];
+      else if (row_ok) src = AMODE == 3 ? (long long)__ldg(p.idx + m * p.T + t) : m;
       if (src >= 0) {
-        const float4* row = reinterpret_cast<const float4*>(p.A + src * p.lda + (p.idx ? 0 : (long long)t * p.K)) + kc * (KC / 4);
-        if (p.a256) {
+        const float4* row = reinterpret_cast<const float4*>(p.A + src * p.lda + (AMODE == 0 ? (long long)t * p.K : 0)) + kc * (KC / 4);
+        if (full_k && p.a256) {
 #pragma unroll
-          for (int j = 0; j < KC / 4; j += 2) {
-            if (j * 4 < kleft) ldg256(reinterpret_cast<const float*>(row + j), v[j], v[j + 1]);   // kleft is a multiple of 8 here
-            else v[j] = v[j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int j = 0; j < KC / 4; j += 2) ldg256(reinterpret_cast<const float*>(row + j), v[j], v[j + 1]);
+        } else if (full_k) {
+#pragma unroll
+          for (int j = 0; j < KC / 4; ++j) v[j] = __ldg(row + j);
         } else {
+          const int kleft = p.K - kc * KC;                                // valid fp32 elements of this chunk (K may be 16 mod 32)
 #pragma unroll
           for (int j = 0; j < KC / 4; ++j) v[j] = j * 4 < kleft ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -257,8 +266,10 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
       }
     };
     // two gathers alternate in registers: iteration it+2 is requested right after iteration it has been stored
+    int pq = 0, pu = 0;                                                  // ring slot / round of the iteration being stored
     auto proc = [&](int it, float4* v) {
-      const int q = it % AT, u = it / AT;
+      const int q = pq, u = pu;
+      if (++pq == AT) { pq = 0; ++pu; }
       uint32_t hi[KC / 2], lo[KC / 2];
 #pragma unroll
       for (int j = 0; j < KC / 4; ++j) {
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
         lo[2 * j] = *reinterpret_cast<const uint32_t*>(&l0); lo[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l1);
       }
       if (tr && threadIdx.x == 0 && it == 0) p.trace[2] = clock64();     // first chunk arrived + converted
-      if (it + 2 < n_iter) fetch(it + 2, v);
+      if (it + 2 < n_iter) fetch(v);
       if (u > 0) {
         mbar_wait(smem_u32(&bars->empty_a[q]), (uint32_t)((u - 1) & 1));
         tc_fence_after();
@@ -282,8 +293,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
       if (tr && threadIdx.x == 0 && it == 0) p.trace[3] = clock64();     // first chunk stored to TMEM + signalled
     };
     float4 v0[KC / 4], v1[KC / 4];
-    if (n_iter > 0) fetch(0, v0);
-    if (n_iter > 1) fetch(1, v1);
+    if (n_iter > 0) fetch(v0);
+    if (n_iter > 1) fetch(v1);
     if (tr && threadIdx.x == 0) p.trace[1] = clock64();                  // first gathers issued
     for (int it = 0; it < n_iter; it += 2) {
       proc(it, v0);
@@ -723,12 +734,18 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   // otherwise the spill-free 2-per-SM build.  CDSEG_GEMM_MINB=2|3 forces one for experiments.
   static const int forced = [] { const char* e = getenv("CDSEG_GEMM_MINB"); return e ? atoi(e) : 0; }();
   const bool dense3 = forced ? forced == 3 : (tmem_cols <= 128 && smem * 3 <= 220 * 1024);
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[dense3]) {
-    cudaError_t e = dense3 ? cudaFuncSetAttribute(gt::gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(gt::gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (!idx && tile_mask) return CDSEG_EINVAL;
+  const int amode = sub ? 2 : (!idx ? 0 : (T <= 32 ? 1 : 3));      // see the kernel's producer section
+  typedef void (*KernelFn)(const gt::Params);
+  static const KernelFn kernels[2][4] = {
+      {gt::gemm_tc_kernel<2, 0>, gt::gemm_tc_kernel<2, 1>, gt::gemm_tc_kernel<2, 2>, gt::gemm_tc_kernel<2, 3>},
+      {gt::gemm_tc_kernel<3, 0>, gt::gemm_tc_kernel<3, 1>, gt::gemm_tc_kernel<3, 2>, gt::gemm_tc_kernel<3, 3>}};
+  const KernelFn kernel = kernels[dense3][amode];
+  static size_t configured[2][4] = {};
+  if (smem > configured[dense3][amode]) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured[dense3] = smem;
+    configured[dense3][amode] = smem;
   }
   gt::Params p;
   p.A = A; p.lda = lda; p.idx = idx; p.T = T; p.tile_mask = tile_mask; p.Bp = Bp; p.sub = sub; p.taps_ld = taps_ld;
@@ -745,8 +762,7 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
               (!res || ((uintptr_t)res & 15) == 0)) ? 1 : 0;
   p.fast_epi = (!no_fast && p.vec_ok && (nw & 31) == 0 && !(((uintptr_t)bias | (uintptr_t)workspace) & 15)) ? 1 : 0;
   dim3 g(cdseg_div_up(M, gt::BM), (N + nw - 1) / nw, nsplit);
-  if (dense3) cdseg_launch_pdl(gt::gemm_tc_kernel<3>, g, dim3(gt::NTHREADS), smem, st, p);
-  else cdseg_launch_pdl(gt::gemm_tc_kernel<2>, g, dim3(gt::NTHREADS), smem, st, p);
+  cdseg_launch_pdl(kernel, g, dim3(gt::NTHREADS), smem, st, p);
   CDSEG_COUNT_LAUNCH(1);
   if (nsplit > 1 && out) {                   // out == NULL: the caller consumes the raw partials part[z][M][N] itself (cdseg_reduce_ln)
     const bool v4 = (N & 3) == 0 && (ldo & 3) == 0 && (!res || (ldr & 3) == 0) &&
