@@ -63,6 +63,12 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// one lane of a converged warp (elect.sync): keeps the surrounding control flow -- and with it the tcgen05 operands -- warp-uniform
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -111,11 +117,12 @@ struct Params {
   int single;                             // 1: fp16 x fp16 products only (hi.hi; the lo terms are skipped): the reduced-precision mode
 };
 
-constexpr int MAX_RING = 4;
+constexpr int MAX_RING = 4;             // A ring slots (TMEM)
+constexpr int MAX_RING_B = 8;           // B ring stages (shared memory): weights depend on nothing, so the loader may run far ahead
 constexpr int STG_BYTES = 4 * 32 * 36 * 4;   // epilogue staging: 4 warps x 32 rows x 36 floats
 
 struct Bars {
-  uint64_t full_a[MAX_RING], empty_a[MAX_RING], full_b[MAX_RING], empty_b[MAX_RING], acc;
+  uint64_t full_a[MAX_RING], empty_a[MAX_RING], full_b[MAX_RING_B], empty_b[MAX_RING_B], acc;
   uint32_t tmem_slot, pad;
   uint8_t taps[32];                       // present taps of this CTA's split, ascending
 };
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
   const int t_begin = (int)((long long)p.T * z / p.nsplit), t_end = (int)((long long)p.T * (z + 1) / p.nsplit);
 
   PDL_TRIGGER_EARLY();
-  if (threadIdx.x < 4 * MAX_RING + 1) {              // one barrier per thread (Bars: full_a, empty_a, full_b, empty_b, acc are contiguous)
+  if (threadIdx.x < 2 * MAX_RING + 2 * MAX_RING_B + 1) {   // one barrier per thread (Bars: full_a, empty_a, full_b, empty_b, acc are contiguous)
     const int b = threadIdx.x;
     mbar_init(smem_u32(&bars->full_a[0]) + 8u * b, b < MAX_RING ? 128u : 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -177,10 +184,12 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  pdl_wait();                                     // nothing above touches global memory
-  const uint32_t mask = p.tile_mask ? p.tile_mask[tile_m] : 0xffffffffu;
+  // Dense mode: the tap list is the identity and the B loader (warp 4) reads weights only, so it skips the wait and streams the first
+  // weight blocks while the preceding kernel of the stream is still finishing; every other thread waits before its first global access.
+  if (AMODE != 0 || warp != 4) pdl_wait();        // nothing above touches global memory
+  const uint32_t mask = (AMODE != 0 && p.tile_mask) ? p.tile_mask[tile_m] : 0xffffffffu;
   int ntap = t_end - t_begin;
-  if (p.T <= 32) {
+  if (AMODE != 0 && p.T <= 32) {
     const uint32_t width = (uint32_t)(t_end - t_begin);
     const uint32_t present = mask & ((width >= 32 ? 0xffffffffu : ((1u << width) - 1u)) << t_begin);
     ntap = __popc(present);
@@ -200,8 +209,8 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
   // present taps of this CTA's split (listed in shared memory by thread 32 before the barrier above)
   // -> iteration it = (tap taps[it / kch], chunk it % kch)
   const int n_iter = ntap * kch;
-  auto tap_of = [&](int it) { const int j = it / kch; return p.T <= 32 ? (int)bars->taps[j] : t_begin + j; };
-  auto tap_of_slot = [&](int j) { return p.T <= 32 ? (int)bars->taps[j] : t_begin + j; };
+  auto tap_of_slot = [&](int j) { return (AMODE != 0 && p.T <= 32) ? (int)bars->taps[j] : t_begin + j; };
+  auto tap_of = [&](int it) { return tap_of_slot(it / kch); };
 
   if (warp < 4) {
     // ------------------------------- A producers -------------------------------
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
     // fetches are requested in iteration order: (tap slot fj, chunk fkc) advance incrementally instead of it / kch, it % kch
     int fj = 0, fkc = 0;
     auto fetch = [&](float4* v) {
-      const int t = AMODE == 0 ? t_begin + fj : tap_of_slot(fj);
+      const int t = tap_of_slot(fj);
       const int kc = fkc;
       if (++fkc == kch) { fkc = 0; ++fj; }
       if (AMODE == 2) {
@@ -432,50 +441,74 @@ __global__ void __launch_bounds__(NTHREADS, MINB) gemm_tc_kernel(const Params p)
     }
   } else if (warp == 4) {
     // -------------------------------- B loader --------------------------------
+    // (this loop and the MMA issuer's run on ONE thread each: every integer division by a runtime ring depth or chunk count costs that
+    // thread ~100 cycles, so stage / phase / tap / chunk advance incrementally -- profiles/r02_microbench_mma_commit.txt)
     if (lane == 0) {
       const uint32_t bbytes = (uint32_t)un * KC * 2;            // prefix of the fp16 hi / lo block (n-groups are outermost)
+      const long long blk_step = (long long)ntiles * 2 * (NT * KC);       // halves between consecutive (tap, chunk) blocks
+      const __half* blk0 = reinterpret_cast<const __half*>(p.Bp) + (long long)(n0 / NT) * 2 * (NT * KC) + (n0 % NT) * KC;
+      int s = 0, kc = 0, j = 0;
+      uint32_t ph = 1;                                           // parity to wait for on empty_b: the first round passes
+      uint32_t b_hi = smem_u32(s_b);
+      const __half* blk = blk0 + (long long)tap_of_slot(0) * kch * blk_step;
       for (int it = 0; it < n_iter; ++it) {
-        const int t = tap_of(it), kc = it - (it / kch) * kch;
-        const int s = it % SB, u = it / SB;
-        if (u > 0) mbar_wait(smem_u32(&bars->empty_b[s]), (uint32_t)((u - 1) & 1));
+        if (it >= SB) mbar_wait(smem_u32(&bars->empty_b[s]), ph);
         // packed block of the 128-column group this tile lies in; a narrower tile starts (n0 % NT) / 8 row-groups of 8 n x 32 k into it
-        const __half* blk = reinterpret_cast<const __half*>(p.Bp) + ((((long long)t * kch + kc) * ntiles + n0 / NT) * 2) * (NT * KC) + (n0 % NT) * KC;
-        uint8_t* b_hi = s_b + (size_t)s * 2 * B_BYTES;
-        mbar_expect_tx(smem_u32(&bars->full_b[s]), 2 * bbytes);
-        tma_load_1d(smem_u32(b_hi), blk, bbytes, smem_u32(&bars->full_b[s]));
-        tma_load_1d(smem_u32(b_hi + B_BYTES), blk + NT * KC, bbytes, smem_u32(&bars->full_b[s]));
+        const uint32_t full = smem_u32(&bars->full_b[s]);
+        mbar_expect_tx(full, 2 * bbytes);
+        tma_load_1d(b_hi, blk, bbytes, full);
+        tma_load_1d(b_hi + B_BYTES, blk + NT * KC, bbytes, full);
+        b_hi += 2 * B_BYTES;
+        if (++s == SB) { s = 0; b_hi = smem_u32(s_b); ph ^= 1; }
+        blk += blk_step;
+        if (++kc == kch) { kc = 0; ++j; if (it + 1 < n_iter) blk = blk0 + (long long)tap_of_slot(j) * kch * blk_step; }
       }
     }
   } else {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0 && n_iter > 0) {
+    // The WHOLE warp runs this loop and one elected lane issues: with `if (lane == 0)` around the loop the operands live in per-lane
+    // registers and the compiler wraps every tcgen05 instruction (a uniform-datapath instruction) in an R2UR + ELECT + BRA.U.ANY
+    // sequence -- ~150 instructions and ~900 cycles per k-iteration for 6 MMAs, slower than the four producer warps deliver A.
+    if (n_iter > 0) {
+      const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_slot, 0);          // warp-uniform copies
+      const uint32_t tmem_a = tmem + (uint32_t)p.acc_cols;
       // kind::f16: D fp32 (1<<4), A = B = F16 (format 0), both K-major, N, M=128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(un >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t dconst = make_desc(0, 128, (KC / 8) * 128);          // + (shared address >> 4) in the low 14 bits
+      int q = 0, s = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t a_hi = tmem_a, b_hi = smem_u32(s_b) >> 4;
+      const uint32_t b_lo_off = (uint32_t)B_BYTES >> 4;
+      const bool single = p.single != 0;
       for (int it = 0; it < n_iter; ++it) {
-        const int q = it % AT, s = it % SB;
-        mbar_wait(smem_u32(&bars->full_a[q]), (uint32_t)((it / AT) & 1));
-        if (tr && it == 0) p.trace[10] = clock64();                      // MMA: A ready
-        mbar_wait(smem_u32(&bars->full_b[s]), (uint32_t)((it / SB) & 1));
-        if (tr && it == 0) p.trace[11] = clock64();                      // MMA: B ready
+        mbar_wait(smem_u32(&bars->full_a[q]), pa);
+        if (tr && it == 0 && lane == 0) p.trace[10] = clock64();         // MMA: A ready
+        mbar_wait(smem_u32(&bars->full_b[s]), pb);
+        if (tr && it == 0 && lane == 0) p.trace[11] = clock64();         // MMA: B ready
         tc_fence_after();
-        const uint32_t a_hi = tmem_a + q * 32, a_lo = a_hi + 16;
-        const uint32_t b_hi = smem_u32(s_b + (size_t)s * 2 * B_BYTES), b_lo = b_hi + B_BYTES;
+        const uint32_t a_lo = a_hi + 16;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < KC / 16; ++ks) {                   // K = 16 per MMA: 8 TMEM columns of A, 2 core matrices (256 B) of B
-          const uint64_t bh = make_desc(b_hi + ks * 256, 128, (KC / 8) * 128), bl = make_desc(b_lo + ks * 256, 128, (KC / 8) * 128);
-          if (p.single) {
-            umma_f16_ts(tmem, a_hi + ks * 8, bh, idesc, (it | ks) != 0);
-          } else {
-            umma_f16_ts(tmem, a_lo + ks * 8, bh, idesc, (it | ks) != 0);   // small terms first
-            umma_f16_ts(tmem, a_hi + ks * 8, bl, idesc, 1);
-            umma_f16_ts(tmem, a_hi + ks * 8, bh, idesc, 1);
+          for (int ks = 0; ks < KC / 16; ++ks) {                 // K = 16 per MMA: 8 TMEM columns of A, 2 core matrices (256 B) of B
+            const uint64_t bh = dconst | (uint64_t)(b_hi + ks * 16), bl = dconst | (uint64_t)(b_hi + b_lo_off + ks * 16);
+            if (single) {
+              umma_f16_ts(tmem, a_hi + ks * 8, bh, idesc, (it | ks) != 0);
+            } else {
+              umma_f16_ts(tmem, a_lo + ks * 8, bh, idesc, (it | ks) != 0);   // small terms first
+              umma_f16_ts(tmem, a_hi + ks * 8, bl, idesc, 1);
+              umma_f16_ts(tmem, a_hi + ks * 8, bh, idesc, 1);
+            }
           }
+          umma_commit(smem_u32(&bars->empty_a[q]));              // each commit tracks every MMA issued so far
+          umma_commit(smem_u32(&bars->empty_b[s]));
         }
-        umma_commit(smem_u32(&bars->empty_a[q]));                // each commit tracks every MMA issued so far
-        umma_commit(smem_u32(&bars->empty_b[s]));
+        __syncwarp();
+        a_hi += 32; b_hi += (uint32_t)(2 * B_BYTES) >> 4;
+        if (++q == AT) { q = 0; a_hi = tmem_a; pa ^= 1; }
+        if (++s == SB) { s = 0; b_hi = smem_u32(s_b) >> 4; pb ^= 1; }
       }
-      umma_commit(smem_u32(&bars->acc));
-      if (tr) p.trace[12] = clock64();                                   // all MMAs issued
+      if (elect_one()) umma_commit(smem_u32(&bars->acc));
+      if (tr && lane == 0) p.trace[12] = clock64();                      // all MMAs issued
     }
   }
   tc_fence_before();
@@ -727,7 +760,9 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   const int AT = acc_cols == 128 ? 4 : ((iters >= 4 && acc_cols <= 32) ? 3 : 2);   // 32+96=128, 64+64=128, 128+128=256 columns
   int tmem_cols = 32;
   while (tmem_cols < acc_cols + AT * 32) tmem_cols <<= 1;
-  const int SB = iters >= 4 ? (un_max <= 64 ? 4 : 3) : 2;
+  // B ring depth: a stage is 2 * b_bytes (4 KB at 32 columns, 16 KB at 128).  Narrow tiles take the whole k-loop in flight: with 4 stages
+  // the MMA thread waited ~1 200 cycles per iteration for weights while the producers delivered A every 700 (r02_trace_gemm_deep_amode.txt)
+  const int SB = iters >= 4 ? (un_max <= 32 ? (iters >= 8 ? 8 : 4) : (un_max <= 64 ? 4 : (iters >= 8 ? 4 : 3))) : 2;
   const size_t smem = (size_t)gt::STG_BYTES + (size_t)SB * 2 * b_bytes + sizeof(gt::Bars) + 64 +
                       ((idx && T <= 32 && !sub) ? (size_t)gt::BM * T * 4 : 0) + 1024;
   // two register budgets: 3+ CTAs per SM (<= 112 registers, a few spills) when TMEM and shared memory allow that many,
