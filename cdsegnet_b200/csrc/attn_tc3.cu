@@ -258,8 +258,11 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    {
       // ------------------------------------- MMA issuer -------------------------------------
+      // whole warp, one elected lane issues (a lane-0 branch around this loop costs an R2UR + ELECT + branch sequence per tcgen05
+      // instruction; see gemm_tc.cu)
+      const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_slot, 0);
       constexpr uint32_t IDESC_S = idesc(NC, false);             // M128 N64, A and B K-major
       constexpr uint32_t IDESC_O = idesc(C::VW, true);           // M128 N32|48, B MN-major
       constexpr uint32_t IDESC_OL = idesc(32, true);             // MODE 1: P_lo . [v_hi | 1]
@@ -273,31 +276,37 @@ attn_tc3_kernel(const __half* __restrict__ Qp, const __half* __restrict__ Kpk, c
           mbar_wait_idle(smem_u32(&bars->kv_full[s]), (uint32_t)((g / R) & 1), sleep_ns);
           if (g >= 1) mbar_wait_idle(smem_u32(&bars->s_free), (uint32_t)((g - 1) & 1), sleep_ns);
           tc_fence_after();
-          const uint32_t kb = smem_u32(sKV + s * C::STAGE);
-          umma_f16(tmem + C::COL_S, qd, make_desc(kb, 128, 256), IDESC_S, 0);
-          if (MODE == 1) {
-            umma_f16(tmem + C::COL_S, qd_lo, make_desc(kb, 128, 256), IDESC_S, 1);
-            umma_f16(tmem + C::COL_S, qd, make_desc(kb + NC * 32, 128, 256), IDESC_S, 1);
+          if (elect_one()) {
+            const uint32_t kb = smem_u32(sKV + s * C::STAGE);
+            umma_f16(tmem + C::COL_S, qd, make_desc(kb, 128, 256), IDESC_S, 0);
+            if (MODE == 1) {
+              umma_f16(tmem + C::COL_S, qd_lo, make_desc(kb, 128, 256), IDESC_S, 1);
+              umma_f16(tmem + C::COL_S, qd, make_desc(kb + NC * 32, 128, 256), IDESC_S, 1);
+            }
+            umma_commit(smem_u32(&bars->s_full));
           }
-          umma_commit(smem_u32(&bars->s_full));
+          __syncwarp();
         }
         if (g >= 1) {                                            // [O | L](g-1) = P . [V | 1]
           const int gp = g - 1, s = gp % R, b = C::DEFER ? (gp & 1) : 0;
           mbar_wait_idle(smem_u32(&bars->p_full[b]), (uint32_t)((C::DEFER ? (gp >> 1) : gp) & 1), sleep_ns);
           tc_fence_after();
-          const uint32_t vb = smem_u32(sKV + s * C::STAGE + C::KBYTES);
-          const uint32_t pb = smem_u32(sP + b * C::SP_ONE);
-          const uint32_t od = tmem + (b ? C::COL_O1 : C::COL_O0);
-#pragma unroll
-          for (int kk = 0; kk < NC / 16; ++kk)
-            if (DBG != 5 || gp == 0) umma_f16(od, make_desc(pb + kk * 2 * 2048, 2048, 128), make_desc(vb + kk * 2 * VKG, VKG, 128), IDESC_O, kk > 0);
-          if (MODE == 1) {
+          if (elect_one()) {
+            const uint32_t vb = smem_u32(sKV + s * C::STAGE + C::KBYTES);
+            const uint32_t pb = smem_u32(sP + b * C::SP_ONE);
+            const uint32_t od = tmem + (b ? C::COL_O1 : C::COL_O0);
 #pragma unroll
             for (int kk = 0; kk < NC / 16; ++kk)
-              umma_f16(od, make_desc(pb + 128 * NC * 2 + kk * 2 * 2048, 2048, 128), make_desc(vb + kk * 2 * VKG, VKG, 128), IDESC_OL, 1);
+              if (DBG != 5 || gp == 0) umma_f16(od, make_desc(pb + kk * 2 * 2048, 2048, 128), make_desc(vb + kk * 2 * VKG, VKG, 128), IDESC_O, kk > 0);
+            if (MODE == 1) {
+#pragma unroll
+              for (int kk = 0; kk < NC / 16; ++kk)
+                umma_f16(od, make_desc(pb + 128 * NC * 2 + kk * 2 * 2048, 2048, 128), make_desc(vb + kk * 2 * VKG, VKG, 128), IDESC_OL, 1);
+            }
+            umma_commit(smem_u32(&bars->o_full[b]));
+            umma_commit(smem_u32(&bars->kv_empty[s]));
           }
-          umma_commit(smem_u32(&bars->o_full[b]));
-          umma_commit(smem_u32(&bars->kv_empty[s]));
+          __syncwarp();
         }
       }
     }

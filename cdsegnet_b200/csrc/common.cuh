@@ -42,6 +42,13 @@ __device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() defau
 extern unsigned long long g_cdseg_launches;
 #define CDSEG_COUNT_LAUNCH(n) (g_cdseg_launches += (n))
 
+// one lane of a converged warp (elect.sync): keeps the surrounding control flow -- and with it the tcgen05 operands -- warp-uniform
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- programmatic dependent launch (PDL) ----
 // Kernels launched through cdseg_launch_pdl carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may be scheduled as soon
 // as every CTA of the preceding kernel of the stream has executed pdl_trigger() (or exited), and they must not touch global memory

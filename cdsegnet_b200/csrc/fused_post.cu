@@ -208,43 +208,50 @@ post_kernel(const PostParams p, const __grid_constant__ CUtensorMap tmO, const _
     }
   } else {
     // =========================================== MMA issuer ===========================================
-    if (lane == 0) {
+    // whole warp, one elected lane issues (see gemm_tc.cu / fused_pre.cu)
+    {
       uint32_t b_it = 0, ar_use[4] = {0, 0, 0, 0}, gf_cnt = 0;
       const uint32_t idC = idesc_f16(C), id128 = idesc_f16(128);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t uACC1 = tm, uACC0 = tm + 128, uH = tm + 128 + C;
+      const bool single = p.single != 0;
       auto a_wait = [&](int k) { mbar_wait(smem_u32(&bars->a_rdy[k]), ar_use[k] & 1); ++ar_use[k]; };
       // one K = 32 chunk: 2 K-steps x (lo.hi + hi.lo + hi.hi), small terms first
       auto chunk = [&](uint32_t d, uint32_t a, uint32_t idesc, bool first) {
         const int s = b_it % P_SB;
         mbar_wait(smem_u32(&bars->b_full[s]), (b_it / P_SB) & 1);
         tc_fence_after();
-        const uint32_t bh = smem_u32(s_b + s * B_STAGE), bl = bh + BLK * 2;
+        if (elect_one()) {
+          const uint32_t bh = smem_u32(s_b + s * B_STAGE), bl = bh + BLK * 2;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t dh = make_desc(bh + ks * 256, 128, 512), dl = make_desc(bl + ks * 256, 128, 512);
-          if (p.single) {
-            umma_f16_ts(d, a + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
-          } else {
-            umma_f16_ts(d, a + 16 + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
-            umma_f16_ts(d, a + ks * 8, dl, idesc, 1u);
-            umma_f16_ts(d, a + ks * 8, dh, idesc, 1u);
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t dh = make_desc(bh + ks * 256, 128, 512), dl = make_desc(bl + ks * 256, 128, 512);
+            if (single) {
+              umma_f16_ts(d, a + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
+            } else {
+              umma_f16_ts(d, a + 16 + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
+              umma_f16_ts(d, a + ks * 8, dl, idesc, 1u);
+              umma_f16_ts(d, a + ks * 8, dh, idesc, 1u);
+            }
           }
+          umma_commit(smem_u32(&bars->b_empty[s]));
         }
-        umma_commit(smem_u32(&bars->b_empty[s]));
+        __syncwarp();
         ++b_it;
       };
+      auto commit_one = [&](uint32_t bar) { if (elect_one()) umma_commit(bar); __syncwarp(); };
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        for (int kc = 0; kc < nc; ++kc) { a_wait(kc); chunk(ACC0, H + kc * 32, idC, kc == 0); }        // GEMM0: proj
-        umma_commit(smem_u32(&bars->acc_done));
+        for (int kc = 0; kc < nc; ++kc) { a_wait(kc); chunk(uACC0, uH + kc * 32, idC, kc == 0); }        // GEMM0: proj
+        commit_one(smem_u32(&bars->acc_done));
         for (int j = 0; j < J; ++j) {
           if (j > 0) { mbar_wait(smem_u32(&bars->g_free), gf_cnt & 1); ++gf_cnt; }
           for (int kc = 0; kc < nc; ++kc) {                                                             // GEMM1: fc1 chunk j
             if (j == 0) a_wait(kc);
-            chunk(ACC1, H + kc * 32, id128, kc == 0);
+            chunk(uACC1, uH + kc * 32, id128, kc == 0);
           }
-          umma_commit(smem_u32(&bars->acc_done));
-          for (int k = 0; k < 4; ++k) { a_wait(k); chunk(ACC0, ACC1 + k * 32, idC, false); }            // GEMM2: fc2, onto x2
-          if (j + 1 < J) umma_commit(smem_u32(&bars->g_free));
-          else umma_commit(smem_u32(&bars->acc_done));
+          commit_one(smem_u32(&bars->acc_done));
+          for (int k = 0; k < 4; ++k) { a_wait(k); chunk(uACC0, uACC1 + k * 32, idC, false); }            // GEMM2: fc2, onto x2
+          commit_one(j + 1 < J ? smem_u32(&bars->g_free) : smem_u32(&bars->acc_done));
         }
       }
     }

@@ -383,48 +383,57 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
     }
   } else {
     // =========================================== MMA issuer ===========================================
-    if (lane == 0) {
+    // the whole warp walks the schedule and one elected lane issues (see gemm_tc.cu: a lane-0 branch around the loop costs an
+    // R2UR + ELECT + branch sequence per tcgen05 instruction, ~900 cycles per 6-MMA chunk on this one thread)
+    {
       uint32_t b_it = 0, a_it = 0, ar_use[4] = {0, 0, 0, 0}, qf_cnt = 0;
       const uint32_t idC = idesc_f16(C);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t uRING = tm, uACCQ = tm, uACCC = tm + 128, uACCL = tm + 128 + C;
+      const bool single = p.single != 0;
       auto a_wait = [&](int k) { mbar_wait(smem_u32(&bars->a_rdy[k]), ar_use[k] & 1); ++ar_use[k]; };
-      auto chunk = [&](uint32_t d, uint32_t a, uint32_t idesc, bool first) {
+      auto chunk = [&](uint32_t d, uint32_t a, uint32_t idesc, bool first, uint32_t extra_commit) {
         const int s = b_it % Q_SB;
         mbar_wait(smem_u32(&bars->b_full[s]), (b_it / Q_SB) & 1);
         tc_fence_after();
-        const uint32_t bh = smem_u32(s_b + s * B_STAGE), bl = bh + BLK * 2;
+        if (elect_one()) {
+          const uint32_t bh = smem_u32(s_b + s * B_STAGE), bl = bh + BLK * 2;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t dh = make_desc(bh + ks * 256, 128, 512), dl = make_desc(bl + ks * 256, 128, 512);
-          if (p.single) {
-            umma_f16_ts(d, a + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
-          } else {
-            umma_f16_ts(d, a + 16 + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
-            umma_f16_ts(d, a + ks * 8, dl, idesc, 1u);
-            umma_f16_ts(d, a + ks * 8, dh, idesc, 1u);
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t dh = make_desc(bh + ks * 256, 128, 512), dl = make_desc(bl + ks * 256, 128, 512);
+            if (single) {
+              umma_f16_ts(d, a + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
+            } else {
+              umma_f16_ts(d, a + 16 + ks * 8, dh, idesc, (first && ks == 0) ? 0u : 1u);
+              umma_f16_ts(d, a + ks * 8, dl, idesc, 1u);
+              umma_f16_ts(d, a + ks * 8, dh, idesc, 1u);
+            }
           }
+          umma_commit(smem_u32(&bars->b_empty[s]));
+          if (extra_commit) umma_commit(extra_commit);
         }
-        umma_commit(smem_u32(&bars->b_empty[s]));
+        __syncwarp();
         ++b_it;
       };
+      auto commit_one = [&](uint32_t bar) { if (elect_one()) umma_commit(bar); __syncwarp(); };
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const int n_conv = __popc(p.tile_mask[tile] & 0x7ffffffu) * nc;
+        const int n_conv = __popc(__shfl_sync(0xffffffffu, p.tile_mask[tile], 0) & 0x7ffffffu) * nc;
         for (int it = 0; it < n_conv; ++it, ++a_it) {                                     // conv
           const int q = a_it % Q_AT;
           mbar_wait(smem_u32(&bars->a_full[q]), (a_it / Q_AT) & 1);
-          chunk(ACCC, RING + q * 32, idC, it == 0);
-          umma_commit(smem_u32(&bars->a_empty[q]));
+          chunk(uACCC, uRING + q * 32, idC, it == 0, smem_u32(&bars->a_empty[q]));
         }
-        umma_commit(smem_u32(&bars->acc_done));
-        for (int kc = 0; kc < nc; ++kc) { a_wait(kc); chunk(ACCL, ACCC + kc * 32, idC, kc == 0); }   // cpe Linear
-        umma_commit(smem_u32(&bars->acc_done));
+        commit_one(smem_u32(&bars->acc_done));
+        for (int kc = 0; kc < nc; ++kc) { a_wait(kc); chunk(uACCL, uACCC + kc * 32, idC, kc == 0, 0u); }   // cpe Linear
+        commit_one(smem_u32(&bars->acc_done));
         for (int j = 0; j < nq; ++j) {                                                                 // qkv, 128 columns at a time
           if (j > 0) { mbar_wait(smem_u32(&bars->q_free), qf_cnt & 1); ++qf_cnt; tc_fence_after(); }
           const uint32_t idq = idesc_f16(min(128, 3 * C - 128 * j));
           for (int kc = 0; kc < nc; ++kc) {
             if (j == 0) a_wait(kc);
-            chunk(ACCQ, ACCL + kc * 32, idq, kc == 0);
+            chunk(uACCQ, uACCL + kc * 32, idq, kc == 0, 0u);
           }
-          umma_commit(smem_u32(&bars->acc_done));
+          commit_one(smem_u32(&bars->acc_done));
         }
       }
     }

@@ -63,12 +63,6 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-// one lane of a converged warp (elect.sync): keeps the surrounding control flow -- and with it the tcgen05 operands -- warp-uniform
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
