@@ -13,6 +13,8 @@ with open(path) as f:
 rows = list(csv.DictReader(lines))
 idx = [i for i, x in enumerate(rows) if "encode_kernel" in x["Kernel Name"]]
 fw = rows[idx[-1]:]
+if len(idx) >= 2 and len(fw) < idx[-1] - idx[-2]:      # capture cut off mid-forward (-c limit): take the last complete one
+    fw = rows[idx[-2]:idx[-1]]
 tot = sum(float(x["Metric Value"]) for x in fw) / 1e3
 print(f"last forward: {len(fw)} launches, {tot:.1f} us serialised")
 name = lambda k: re.sub(r"\(.*", "", k).replace("void ", "")[:44]

@@ -1,0 +1,7 @@
+python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py tests/test_gpu_full_config.py -x -q -m gpu > gpurun_out/t41.log 2>&1; tail -2 gpurun_out/t40.log
+python profiles/time_attention_r2.py > gpurun_out/time_attention41.txt 2>&1; tail -12 gpurun_out/time_attention41.txt
+python profiles/time_fused.py > gpurun_out/time_fused41.txt 2>&1; tail -8 gpurun_out/time_fused41.txt
+for i in 1 2; do
+  python bench.py --no-cpu --steps 20 > gpurun_out/bench41.log 2>&1
+  echo "bench: $(tail -1 gpurun_out/bench41.log | python -c 'import json,sys; d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["ms_per_step_median"], d["e2e"]["ms_per_step"], d.get("attention_f16",{}).get("ms_per_step"))')"
+done
