@@ -66,6 +66,8 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
   int16_t* s_lidx = reinterpret_cast<int16_t*>(s_b + Q_SB * B_STAGE);
   float* s_par = reinterpret_cast<float*>(s_b + Q_SB * B_STAGE + Q_LIDX);
   PreBars* bars = reinterpret_cast<PreBars*>(s_par + Q_PAR);
+  // 128 zero bytes: the operand row of an absent neighbour, so that the tap loop reads "some row" without a divergent branch
+  const uint8_t* s_zero = reinterpret_cast<const uint8_t*>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~(uintptr_t)15);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.C, nc = C / KC, nq = p.nq;
   float *s_bc = s_par, *s_bl = s_par + C, *s_cg = s_par + 2 * C, *s_cb = s_par + 3 * C, *s_g1 = s_par + 4 * C, *s_b1 = s_par + 5 * C,
@@ -87,6 +89,7 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
     s_bc[i] = p.b_conv[i]; s_bl[i] = p.b_lin[i]; s_cg[i] = p.cpe_g[i]; s_cb[i] = p.cpe_b[i]; s_g1[i] = p.n1_g[i]; s_b1[i] = p.n1_b[i];
   }
   for (int i = threadIdx.x; i < 3 * C; i += Q_THREADS) s_bq[i] = p.b_qkv[i];
+  if (threadIdx.x < 32) reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(s_zero))[threadIdx.x] = 0u;
   if (warp == 6) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)),
                  "r"((uint32_t)p.tmem_cols) : "memory");
@@ -169,17 +172,14 @@ pre_kernel(const PreParams p, const __grid_constant__ CUtensorMap tmG, const __g
           const int t = __ffs(mk) - 1;
           uint32_t w[32];
           if (cached) {
+            // absent neighbour (li < 0): read the zero row -- one uniform path for the warp (about half of a tile's rows miss any
+            // given tap on a surface scan, so the branchy version executed both sides nearly every time)
             const int li = s_lidx[r * 27 + t];
-            if (li >= 0) {
-              const uint8_t* row = s_cache + li * 128;
+            const uint8_t* row = li >= 0 ? s_cache + li * 128 : s_zero;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint4 q4 = *reinterpret_cast<const uint4*>(row + ((j ^ (li & 7)) << 4));
-                w[4 * j] = q4.x; w[4 * j + 1] = q4.y; w[4 * j + 2] = q4.z; w[4 * j + 3] = q4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) w[j] = 0u;
+            for (int j = 0; j < 8; ++j) {
+              const uint4 q4 = *reinterpret_cast<const uint4*>(row + ((j ^ (li & 7)) << 4));
+              w[4 * j] = q4.x; w[4 * j + 1] = q4.y; w[4 * j + 2] = q4.z; w[4 * j + 3] = q4.w;
             }
           } else {
             const int g = m < p.M ? __ldg(p.nbr + m * 27 + t) : -1;
@@ -556,7 +556,7 @@ CDSEG_API int cdseg_pre_attn(const float* conv_in, const float* x, int64_t n, in
   p.trace = g_pre_trace; p.trace_cta = g_pre_trace_cta;
   p.single = g_cdseg_gemm_single;
   const int per_sm = (C <= 64 && !excl) ? 2 : 1;
-  size_t smem = (size_t)fz::Q_CACHE + (size_t)fz::Q_SB * fz::B_STAGE + fz::Q_LIDX + fz::Q_PAR * 4 + sizeof(fz::PreBars) + 1024;
+  size_t smem = (size_t)fz::Q_CACHE + (size_t)fz::Q_SB * fz::B_STAGE + fz::Q_LIDX + fz::Q_PAR * 4 + sizeof(fz::PreBars) + 144 + 1024;
   if (per_sm == 1) smem = smem > 120 * 1024 ? smem : 120 * 1024;
   static size_t configured = 0;
   if (smem > configured) {

@@ -621,6 +621,8 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
     }
     ws[k][c] = w;
   }
+  pdl_trigger();
+  pdl_wait();                      // the weight decode above reads parameters only; A / res / out come from the stream's earlier kernels
   for (int i = tid; i < SK_ROWS * (K / 4); i += 256) {
     const int r = i / (K / 4), q = i % (K / 4);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -731,8 +733,8 @@ static int gemm_tc_launch(const float* A, int64_t lda, const int32_t* idx, int T
   static const bool no_skinny = [] { const char* e = getenv("CDSEG_NO_SKINNY"); return e && atoi(e) != 0; }();
   if (!idx && T == 1 && !sub && nsplit == 1 && out && (K == 32 || K == 64) && M >= 16384 && !no_skinny && !g_cdseg_gemm_single) {
     dim3 g(cdseg_div_up(M, K == 32 ? 128 : 64), cdseg_div_up(N, gt::SK_COLS));
-    if (K == 32) gt::skinny_linear_kernel<32, 128><<<g, 256, 0, st>>>(A, lda, reinterpret_cast<const __half*>(Bp), (int)M, N, bias, res, ldr, act, out, ldo);
-    else gt::skinny_linear_kernel<64, 64><<<g, 256, 0, st>>>(A, lda, reinterpret_cast<const __half*>(Bp), (int)M, N, bias, res, ldr, act, out, ldo);
+    if (K == 32) cdseg_launch_pdl(gt::skinny_linear_kernel<32, 128>, g, dim3(256), 0, st, A, (long long)lda, reinterpret_cast<const __half*>(Bp), (int)M, N, bias, res, (long long)ldr, act, out, (long long)ldo);
+    else cdseg_launch_pdl(gt::skinny_linear_kernel<64, 64>, g, dim3(256), 0, st, A, (long long)lda, reinterpret_cast<const __half*>(Bp), (int)M, N, bias, res, (long long)ldr, act, out, (long long)ldo);
     CDSEG_COUNT_LAUNCH(1);
     CDSEG_LAUNCH_CHECK();
     return CDSEG_OK;

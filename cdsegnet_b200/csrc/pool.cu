@@ -195,6 +195,8 @@ __global__ void pool_reduce_kernel(const float* __restrict__ x, const float* __r
                                    const int32_t* __restrict__ members, const int32_t* __restrict__ idx_ptr,
                                    int64_t m, int C, const float* __restrict__ scale, const float* __restrict__ shift,
                                    int gelu, float* __restrict__ out, float* __restrict__ out_coord) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= m) return;
@@ -218,9 +220,8 @@ CDSEG_API int cdseg_pool_reduce(const float* x, const float* coord, const int32_
                                 float* out_coord, void* stream) {
   if (C <= 0) return CDSEG_EINVAL;
   if (m == 0) return CDSEG_OK;
-  pool_reduce_kernel<<<cdseg_div_up(m * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, coord, members, idx_ptr, m, C,
-                                                                                 bn_scale, bn_shift, gelu, out,
-                                                                                 out_coord);
+  cdseg_launch_pdl(pool_reduce_kernel, dim3(cdseg_div_up(m * 32, 256)), dim3(256), 0, (cudaStream_t)stream, x, coord, members, idx_ptr, m, C,
+                   bn_scale, bn_shift, gelu, out, out_coord);
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;
@@ -232,6 +233,8 @@ CDSEG_API int cdseg_pool_reduce(const float* x, const float* coord, const int32_
 __global__ void unpool_add_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                   const int32_t* __restrict__ cluster, int64_t n, int C4, float alpha,
                                   float4* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= n * C4) return;
   const int64_t i = t / C4;
@@ -244,8 +247,8 @@ CDSEG_API int cdseg_unpool_add(const float* a, const float* b, const int32_t* cl
                                float* out, void* stream) {
   if (C <= 0 || (C & 3)) return CDSEG_EINVAL;
   if (n == 0) return CDSEG_OK;
-  unpool_add_kernel<<<cdseg_div_up(n * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)a, (const float4*)b, cluster, n, C / 4, alpha, (float4*)out);
+  cdseg_launch_pdl(unpool_add_kernel, dim3(cdseg_div_up(n * (C / 4), 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)a,
+                   (const float4*)b, cluster, n, C / 4, alpha, (float4*)out);
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;
