@@ -248,3 +248,36 @@ def test_native_net_single_stream_and_repeat():
             assert np.abs(c["feat"].cpu().numpy() - z["c_feat"]).max() < 1e-3
             for key in ("serialized_code", "serialized_order", "serialized_inverse"):
                 assert np.array_equal(n[key].cpu().numpy(), z[key]), key
+
+
+def test_schedule_switches_do_not_change_the_logits():
+    """priority streams, plan tables on the aux stream (+ deferred pooled-level launches) and programmatic dependent launch only move
+    WHEN kernels run: every combination gives bit-identical logits, forward after forward (a missing dependency shows up as a diff)"""
+    import itertools
+    z, cfg, shapes = load_case("case2_batch2")
+    import cdsegnet_b200 as cb
+    from cdsegnet_b200 import _lib
+    from cdsegnet_b200.segmentor import calc_t_emb
+    lib = _lib.load()
+    m = cb.PointTransformerV3(**dict(cfg, enable_flash=False))
+    m.load_state_dict(synth_state_dict(shapes), strict=True)
+    m = m.to(DEV).eval()
+    base = dict(coord=t(z["coord"]).to(DEV), grid_coord=t(z["grid_coord"]).to(DEV), offset=t(z["offset"]).to(DEV))
+    ts = 999 * torch.ones((len(z["coord"]), 1), dtype=torch.int64, device=DEV)
+    ref = None
+    pdl0 = lib.cdseg_get_pdl()
+    try:
+        for prio, aux, pdl in itertools.product((False, True), (False, True), (0, 1)):
+            m.priority_streams, m.plan_aux_stream = prio, aux
+            lib.cdseg_set_pdl(pdl)
+            for _ in range(2):
+                c, n = m(dict(base, feat=t(z["noise"]).to(DEV), t_emb=calc_t_emb(ts, 128)), dict(base, feat=t(z["feat"]).to(DEV)),
+                         perm_fn=replay(z["perms"]))
+                torch.cuda.synchronize()
+                out = (n["feat"].cpu().numpy(), c["feat"].cpu().numpy())
+                if ref is None:
+                    ref = out
+                    assert np.abs(out[0] - z["n_feat"]).max() < 1e-3
+                assert np.array_equal(out[0], ref[0]) and np.array_equal(out[1], ref[1]), (prio, aux, pdl)
+    finally:
+        lib.cdseg_set_pdl(pdl0)
