@@ -19,6 +19,18 @@ inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int pick_split(int64_t tiles, int T) {
   if (tiles >= 120 || T == 1) return 1;
+  if (T == 27) {
+    // 27-tap convs at the deep levels: CTAs per launch = tiles * s on 2 x 148 resident slots.  The divisor rule below picked s = 9 for
+    // 48 tiles (432 CTAs = 1.46 waves of 3 taps); an uneven split that fills ONE wave (s = 6: 288 CTAs of 4-5 taps) is shorter.
+    // cost(s) = waves * (taps per CTA + 1 tap-time of prologue / epilogue)
+    int best = 1;
+    long long best_cost = -1;
+    for (int s = 1; s <= T; ++s) {
+      const long long waves = (tiles * s + 295) / 296, cost = waves * ((T + s - 1) / s + 1);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+    }
+    return best;
+  }
   const int want = (int)((200 + tiles - 1) / tiles);
   for (int s = 1; s <= T; ++s)
     if (T % s == 0 && s >= want) return s;

@@ -402,6 +402,13 @@ def pick_split(tiles, T):
     leave most of the 148 SMs idle while one CTA streams the whole weight)"""
     if tiles >= 120 or T == 1:
         return 1
+    if T == 27:      # deep-level convs: the (possibly uneven) split that fills one wave of 2 x 148 CTAs; same rule as csrc/net_exec.cu
+        best, best_cost = 1, None
+        for s in range(1, T + 1):
+            cost = -(-tiles * s // 296) * (-(-T // s) + 1)
+            if best_cost is None or cost < best_cost:
+                best, best_cost = s, cost
+        return best
     want = -(-200 // tiles)
     for s in range(1, T + 1):
         if T % s == 0 and s >= want:
