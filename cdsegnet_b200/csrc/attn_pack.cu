@@ -41,8 +41,18 @@ __global__ void pack_heads_kernel(const float* __restrict__ src, int64_t ld, int
   float v[16];
   if (s >= 0) {
     const float4* row = reinterpret_cast<const float4*>(src + (int64_t)s * ld + col0 + which * C + h * 16);
+    float4 q[4];
+    // every lane reads a different row: 32-byte loads halve the L1 wavefronts (callers pass 64-byte aligned head columns; the check
+    // covers the base pointer and the row stride)
+    if ((((uintptr_t)src | (uintptr_t)(ld * 4) | (uintptr_t)(col0 * 4) | (uintptr_t)(C * 4)) & 31) == 0) {
+      ldg256(reinterpret_cast<const float*>(row), q[0], q[1]);
+      ldg256(reinterpret_cast<const float*>(row + 2), q[2], q[3]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { float4 q = row[j]; v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w; }
+      for (int j = 0; j < 4; ++j) q[j] = row[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[4 * j] = q[j].x; v[4 * j + 1] = q[j].y; v[4 * j + 2] = q[j].z; v[4 * j + 3] = q[j].w; }
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -103,7 +113,7 @@ CDSEG_API int cdseg_attn_pack_f16v(const float* src, int64_t ld, int col0, int C
 // per key, [v_hi(16) | 1 | 0 x 15 | v_lo(16)], block layout (k/8)*384 + (n/8)*64 + (k%8)*8 + n%8 (MN-major B operand).
 __global__ void pack_split_kernel(const float* __restrict__ src, int64_t ld, int col0, int C, int nwhich,
                                   const int32_t* __restrict__ slot_src, int H, int T, int Kp, __half* __restrict__ dst0,
-                                  __half* __restrict__ dst1, __half* __restrict__ dst2, int v_which) {
+                                  __half* __restrict__ dst1, __half* __restrict__ dst2, int v_which, int a256) {
   pdl_trigger();
   pdl_wait();
   const int64_t slots = (int64_t)T * Kp;
@@ -117,8 +127,16 @@ __global__ void pack_split_kernel(const float* __restrict__ src, int64_t ld, int
   float v[16];
   if (s >= 0) {
     const float4* row = reinterpret_cast<const float4*>(src + (int64_t)s * ld + col0 + which * C + h * 16);
+    float4 q[4];
+    if (a256) {               // every lane reads a different row: 32-byte loads halve the L1 wavefronts (see gemm_tc.cu)
+      ldg256(reinterpret_cast<const float*>(row), q[0], q[1]);
+      ldg256(reinterpret_cast<const float*>(row + 2), q[2], q[3]);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { float4 q = row[j]; v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w; }
+      for (int j = 0; j < 4; ++j) q[j] = row[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[4 * j] = q[j].x; v[4 * j + 1] = q[j].y; v[4 * j + 2] = q[j].z; v[4 * j + 3] = q[j].w; }
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -155,7 +173,8 @@ CDSEG_API int cdseg_attn_pack_split(const float* src, int64_t ld, int col0, int 
   const int64_t total = (int64_t)T * Kp * H * nwhich;
   if (total == 0) return CDSEG_OK;
   cdseg_launch_pdl(pack_split_kernel, dim3(cdseg_div_up(total, 256)), dim3(256), 0, (cudaStream_t)stream, src, ld, col0, C, nwhich, slot_src,
-                   H, T, Kp, (__half*)dst0, (__half*)dst1, (__half*)dst2, has_v ? nwhich - 1 : -1);
+                   H, T, Kp, (__half*)dst0, (__half*)dst1, (__half*)dst2, has_v ? nwhich - 1 : -1,
+                   (((uintptr_t)src & 31) == 0 && (ld & 7) == 0 && (col0 & 7) == 0 && (C & 7) == 0) ? 1 : 0);
   CDSEG_COUNT_LAUNCH(1);
   CDSEG_LAUNCH_CHECK();
   return CDSEG_OK;

@@ -42,6 +42,15 @@ __device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() defau
 extern unsigned long long g_cdseg_launches;
 #define CDSEG_COUNT_LAUNCH(n) (g_cdseg_launches += (n))
 
+// 256-bit read-only global load (sm_100: LDG.256).  The A gather has every lane of a warp on a different row, so each warp-level load
+// costs one L1 wavefront per lane whatever its width: 32-byte loads halve the wavefronts per k-chunk, which is what bounds the deep
+// levels' launches (profiles/r02_trace_gemm_deep.txt: 1 200 - 1 800 cycles per k-iteration with four producer warps per SM).
+__device__ __forceinline__ void ldg256(const float* ptr, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(ptr));
+}
+
 // one lane of a converged warp (elect.sync): keeps the surrounding control flow -- and with it the tcgen05 operands -- warp-uniform
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

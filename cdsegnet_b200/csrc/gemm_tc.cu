@@ -121,15 +121,6 @@ struct Bars {
   uint8_t taps[32];                       // present taps of this CTA's split, ascending
 };
 
-// 256-bit read-only global load (sm_100: LDG.256).  The A gather has every lane of a warp on a different row, so each warp-level load
-// costs one L1 wavefront per lane whatever its width: 32-byte loads halve the wavefronts per k-chunk, which is what bounds the deep
-// levels' launches (profiles/r02_trace_gemm_deep.txt: 1 200 - 1 800 cycles per k-iteration with four producer warps per SM).
-__device__ __forceinline__ void ldg256(const float* ptr, float4& a, float4& b) {
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-               : "l"(ptr));
-}
-
 // D[tmem] (+)= A[tmem] . B[smem]   (A: lane = row, two fp16 K elements per 32-bit column)
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
