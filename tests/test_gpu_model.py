@@ -229,7 +229,7 @@ def test_native_net_executor_equals_per_module_path(name, mode):
 
 
 def test_native_net_single_stream_and_repeat():
-    """native executor, repeated forwards on recycled arenas; the two-stream schedule (off by default, see ptv3.py) on this small case"""
+    """native executor, repeated forwards on recycled arenas; single stream and the default two-stream schedule on this small case"""
     z, cfg, shapes = load_case("case2_batch2")
     import cdsegnet_b200 as cb
     from cdsegnet_b200.segmentor import calc_t_emb
