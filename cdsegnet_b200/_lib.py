@@ -152,6 +152,8 @@ SIGNATURES = {
     "cdseg_conv_tile_plan": (_I, [_P, _L, _P, _P]),
     "cdseg_plan_arena_bytes": (_Z, [_L, _I, _I, _I, _I, _I, _I, _I]),
     "cdseg_plan_finish": (_I, []),
+    "cdseg_debug_pick_split": (_I, [_L, _I]),
+    "cdseg_debug_pick_split_block": (_I, [_L, _I]),
     "cdseg_plan_build": (_I, [_P, _P, _L, _I, ctypes.POINTER(_I), _I, ctypes.POINTER(PlanLevel), _I, _P, _I, ctypes.POINTER(ctypes.c_int32), _P, _Z, _P, _P]),
     "cdseg_net_arena_bytes": (_I, [_P, ctypes.POINTER(_Z), ctypes.POINTER(_Z)]),
     "cdseg_net_forward": (_I, [_P]),

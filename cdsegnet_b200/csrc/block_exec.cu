@@ -30,6 +30,8 @@ static int pick_split(int64_t tiles, int T) {
   return T;
 }
 
+CDSEG_API int cdseg_debug_pick_split_block(int64_t tiles, int T) { return pick_split(tiles, T); }   // see net_exec.cu
+
 struct Gemm { const float* Bp; const float* bias; };
 
 static int g_fused_mask = 0x7fffffff;

@@ -404,6 +404,10 @@ void totals(const CdsegForwardArgs* a, const Sizes& z, size_t* m, size_t* s) {
 // bit 2 log every arena allocation to stderr
 CDSEG_API void cdseg_net_set_debug(int flags) { g_net_debug = flags; }
 
+// the split heuristic of this file (block_exec.cu and cdsegnet_b200/ops.py::pick_split carry copies: the three launch paths must make the
+// same choice to stay bit-identical; tests/test_cpu_oracle.py compares them through this export)
+CDSEG_API int cdseg_debug_pick_split(int64_t tiles, int T) { return pick_split(tiles, T); }
+
 CDSEG_API int cdseg_net_arena_bytes(const CdsegForwardArgs* args, size_t* main_bytes, size_t* side_bytes) {
   Sizes z{};
   const int st = walk(args, true, &z);

@@ -323,6 +323,9 @@ void cdseg_net_set_debug(int flags);
 /* sizeof(CdsegBlockArgs, CdsegPatchMap, CdsegPlanLevel, CdsegLinW, CdsegLnW, CdsegBlockW, CdsegPoolW, CdsegUnpoolW, CdsegStageW, CdsegStemW,
  * CdsegCrossW, CdsegNetW, CdsegForwardArgs) in that order; returns how many there are.  For bindings to check their struct mirrors. */
 int cdseg_struct_sizes(size_t* out, int n);
+/* test hooks: the split-K / tap-split heuristic of net_exec.cu and block_exec.cu (must equal cdsegnet_b200/ops.py::pick_split) */
+int cdseg_debug_pick_split(int64_t tiles, int T);
+int cdseg_debug_pick_split_block(int64_t tiles, int T);
 
 /* CUDA events for live per-kernel timing inside the timed region (bench.py) */
 void* cdseg_event_create(void);

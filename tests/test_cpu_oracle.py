@@ -160,3 +160,14 @@ def test_ctypes_struct_mirrors_match_the_c_layouts(lib):
     assert n == len(mirrors)
     for i, m in enumerate(mirrors):
         assert ctypes.sizeof(m) == out[i], (m.__name__, ctypes.sizeof(m), out[i])
+
+
+def test_split_heuristic_is_the_same_on_all_three_launch_paths(lib):
+    """net_exec.cu, block_exec.cu and the per-module Python path each pick the split-K / tap-split of a launch; the summation order --
+    and with it bit-identity between the paths -- depends on all three agreeing"""
+    from cdsegnet_b200 import ops
+    for T in (1, 4, 8, 16, 27, 32):
+        for tiles in list(range(1, 130)) + [200, 938]:
+            a, b, c = lib.cdseg_debug_pick_split(tiles, T), lib.cdseg_debug_pick_split_block(tiles, T), ops.pick_split(tiles, T)
+            assert a == b == c, (tiles, T, a, b, c)
+            assert 1 <= a <= T
