@@ -285,7 +285,7 @@ float* cross_block(Ctx& c, const CdsegCrossW& w, const CdsegPlanLevel& Lq, const
   return out;
 }
 
-cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+cudaEvent_t g_ev_all[16][4] = {};                 // fork / join events, one set per device of the process
 
 struct Sizes { size_t act_m, act_s, scratch_m, ws_m, scratch_s, ws_s; };
 
@@ -300,6 +300,9 @@ int walk(const CdsegForwardArgs* a, bool dry, Sizes* sz) {
   const bool two = w.condition && a->stream_side && a->stream_side != a->stream_main;
   if (two && !dry && !a->arena_side) return CDSEG_EINVAL;
   cudaStream_t sm = (cudaStream_t)a->stream_main, ss = two ? (cudaStream_t)a->stream_side : sm;
+  int dev_id = 0;
+  if (two && !dry && (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 16)) return (int)cudaErrorUnknown;
+  cudaEvent_t* g_ev = g_ev_all[dev_id];
   if (two && !dry && !g_ev[0])
     for (int i = 0; i < 4; ++i)
       if (cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming) != cudaSuccess) return (int)cudaErrorUnknown;

@@ -59,11 +59,14 @@ static void* stage(size_t bytes) {
 // events of the aux-stream schedule: one per level (tables complete), one for the stem table, two forks.  Static: a later plan's
 // records land later on the same in-order aux stream, so a consumer that waits on a re-recorded event only over-waits.
 enum { MAX_LV = 16 };
-static cudaEvent_t g_pev[MAX_LV + 3] = {};
-static bool plan_events() {
-  for (auto& e : g_pev)
-    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
-  return true;
+enum { MAX_DEV = 16 };
+static cudaEvent_t g_pev_all[MAX_DEV][MAX_LV + 3] = {};         // events belong to a device: one set per device of the process
+static cudaEvent_t* plan_events() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+  for (auto& e : g_pev_all[dev])
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  return g_pev_all[dev];
 }
 
 // Launches of the pooled levels' tables and slot maps that an aux-stream build leaves for cdseg_plan_finish(): after the second host sync
@@ -71,13 +74,18 @@ static bool plan_events() {
 // network -- cdseg_net_forward enqueues the stems and the level-0 stage first and calls cdseg_plan_finish() before its first pooled
 // stage (profiles/r02_timeline.md).  One plan at a time per process (the list is static); a new build flushes what is left.
 static std::vector<std::function<int()>> g_pending;
+static int g_pending_dev = -1;                                   // device the pending launches belong to
 CDSEG_API int cdseg_plan_finish(void) {
-  int rc = CDSEG_OK;
+  if (g_pending.empty()) return CDSEG_OK;
+  int cur = 0, rc = CDSEG_OK;
+  cudaGetDevice(&cur);
+  if (g_pending_dev >= 0 && g_pending_dev != cur) cudaSetDevice(g_pending_dev);
   for (auto& f : g_pending) {
     const int r = f();
     if (rc == CDSEG_OK) rc = r;
   }
   g_pending.clear();
+  if (g_pending_dev >= 0 && g_pending_dev != cur) cudaSetDevice(cur);
   return rc;
 }
 
@@ -94,7 +102,8 @@ CDSEG_API int cdseg_plan_build(const int32_t* grid, const int64_t* offset, int64
   // pooling hierarchy and beside the first kernels of the forward; consumers wait on the per-level `ready` events.
   const bool two = aux_stream && aux_stream != stream;
   cudaStream_t sa = two ? (cudaStream_t)aux_stream : st;
-  if (two && !plan_events()) return (int)cudaErrorUnknown;
+  cudaEvent_t* g_pev = two ? plan_events() : nullptr;
+  if (two && !g_pev) return (int)cudaErrorUnknown;
   if (!g_pending.empty()) { const int r = cdseg_plan_finish(); if (r != CDSEG_OK) return r; }
   bool defer = false;                                              // set after the second sync (pooled levels only)
   char* p = (char*)arena;
@@ -273,6 +282,7 @@ CDSEG_API int cdseg_plan_build(const int32_t* grid, const int64_t* offset, int64
   // ---------------- tables of the pooled levels + patch slot maps ----------------
   if (two) { cudaEventRecord(g_pev[MAX_LV + 2], st); cudaStreamWaitEvent(sa, g_pev[MAX_LV + 2], 0); }     // the pooled grids come from `st`
   defer = two;
+  if (defer) cudaGetDevice(&g_pending_dev);
   for (int i = 0; i < n_lv; ++i) {
     CdsegPlanLevel& L = lv[i];
     if (L.parent >= 0) RUN(build_tables(i));
