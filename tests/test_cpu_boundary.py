@@ -100,3 +100,23 @@ print("LIVE-OK")
 def test_live_registration_into_the_reference_registry():
     r = subprocess.run([sys.executable, "-c", f"ROOT = {ROOT!r}\n" + LIVE], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "LIVE-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_the_c_example_of_integration_md_compiles_against_the_header(tmp_path):
+    """INTEGRATION.md shows the two-call forward from a C host; the snippet must stay valid C against include/cdseg_b200.h"""
+    import re, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    m = re.search(r"```c\n(.*?)```", md, re.S)
+    assert m, "INTEGRATION.md lost its C example"
+    body = "\n".join(l for l in m.group(1).splitlines() if not l.startswith("#include"))
+    src = ('#include <stddef.h>\n#include "cdseg_b200.h"\n'
+           "int demo(const int32_t* grid, const int64_t* offset, int64_t N, int B, const int* order_ids, CdsegNetW netw, void* plan_arena,\n"
+           "         size_t pb_unused, const float* feat, const float* noisy_target, const float* t_rows, float* logits, float* noise_pred,\n"
+           "         void* stream_hi, void* stream_lo, void* stream_aux) {\n" + body + "\n  return 0;\n}\n")
+    f = tmp_path / "integration_example.c"
+    f.write_text(src)
+    r = subprocess.run(["gcc", "-fsyntax-only", "-std=c99", "-I", os.path.join(root, "include"), str(f)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
